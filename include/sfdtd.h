@@ -1,0 +1,123 @@
+/*
+ * sfdtd.h -- C ABI of the B200-native StringFDTD time stepper (libsfdtd.so).
+ *
+ * This is the drop-in boundary for the reference's only native entry point,
+ *
+ *   vector<Tensor> forward_fn(state_u, state_z, string_params, bow_params,
+ *                             hammer_params, bow_mask, hammer_mask, constant,
+ *                             relative_error, surface_integral, manufactured,
+ *                             n_0, Nt)
+ *   (reference src/model/cpp/simulator.cpp:14-27, bound with pybind11 at :61-63,
+ *    loaded by torch.utils.cpp_extension.load at src/task/simulate.py:28-36 and
+ *    called at src/task/simulate.py:65-76).
+ *
+ * Plain pointers, sizes and strides only -- no torch types.  All data pointers
+ * are DEVICE pointers (CUDA, same device as the current context).  Every array
+ * has its own element strides so that the reference's `narrow()`ed chunk views
+ * (src/task/simulate.py:38-55) and compact inputs with a constant time axis
+ * (time stride 0) are both expressible without copies.
+ *
+ * Semantics follow reference src/model/cpp/string.cpp:43-306 step by step (see
+ * DESIGN.md); "group" = the strings of one reference batch: they share the
+ * batch-max operator widths (misc.cpp:119-127) and the any-over-batch
+ * convergence votes (string.cpp:252-253, hammer.cpp:51).
+ */
+#ifndef SFDTD_H_
+#define SFDTD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFDTD_ABI_VERSION 1
+
+/* dtype of all floating-point arrays */
+enum { SFDTD_F64 = 0 };
+
+/* flags */
+enum {
+    SFDTD_SURFACE_INTEGRAL = 1u << 0, /* pickup = surface integral of velocities (string.cpp:274-291), else interpolated pickup at `pos` (:293-298) */
+    SFDTD_MANUFACTURED     = 1u << 1, /* add the manufactured-solution forcing (vnv.cpp:11-37, string.cpp:227-232) */
+    SFDTD_SAVE_STATE       = 1u << 2, /* state_u/state_z hold the full (B,Nt,Nx) history: row n is read-modified-written in place
+                                         every step like the reference (string.cpp:264-265).  Without it they hold 2 time rows
+                                         [n-2, n-1] per string: read at the start, overwritten with the last two rows at the end. */
+    SFDTD_SKIP_AUX         = 1u << 3  /* do not evaluate v_r for un-bowed strings nor F_H/u_H for un-hammered strings (they are
+                                         written as 0); audio outputs are unaffected.  Off = reference-faithful. */
+};
+
+/* per-string status bits written to `status` (may be NULL) */
+enum {
+    SFDTD_ST_SOLVER_CAP = 1u << 0, /* inner linear iteration hit its cap (result of that step not converged) */
+    SFDTD_ST_OUTER_CAP  = 1u << 1, /* fixed-point loop (string.cpp:200) hit max_iter -- the reference would spin forever */
+    SFDTD_ST_HAMMER_CAP = 1u << 2, /* hammer loop (hammer.cpp:33) hit max_iter */
+    SFDTD_ST_BOW_WINDOW = 1u << 3, /* raised-cosine support wider than the kernel supports */
+    SFDTD_ST_RANGE      = 1u << 4  /* a grid size left the range the launch was sized for */
+};
+
+/* return codes of sfdtd_forward */
+enum {
+    SFDTD_OK = 0,
+    SFDTD_ERR_ARG = -1,        /* bad argument (null pointer, size, dtype, abi) */
+    SFDTD_ERR_UNSUPPORTED = -2,/* configuration outside the built kernel set (grid too wide, group too large) */
+    SFDTD_ERR_CUDA = -3        /* CUDA runtime error; see sfdtd_last_error() */
+};
+
+typedef struct sfdtd_array {
+    void   *ptr;   /* device pointer, may be NULL only where stated */
+    int64_t bs;    /* element stride between strings (batch axis) */
+    int64_t ts;    /* element stride between time samples (0 = constant in time); ignored for per-string scalars */
+} sfdtd_array;
+
+typedef struct sfdtd_args {
+    int32_t abi_version;   /* SFDTD_ABI_VERSION */
+    int32_t dtype;         /* SFDTD_F64 */
+    uint32_t flags;
+    int32_t B;             /* number of strings */
+    int32_t group_size;    /* strings per group (reference batch); groups are consecutive; the last may be short */
+    int32_t Nt;            /* time samples in this call; steps n = 2 .. Nt-1 are computed (simulator.cpp:40) */
+    int32_t Nx_t1, Nx_l1;  /* padded state widths = state_u.size(-1), state_z.size(-1) (string.cpp:123-124) */
+    int32_t n_0;           /* global index of local sample 0 (simulator.cpp:26; only used by MANUFACTURED) */
+    int32_t max_iter;      /* cap for the reference's uncapped loops; <=0 -> 1000 */
+    /* `constant` and `relative_error` arrive as float32 in the reference (simulator.cpp:22-23) */
+    float k, theta_t, lambda_c, relative_order;
+
+    /* states (space stride 1).  SAVE_STATE: (B,Nt,Nx) in/out.  else (B,2,Nx) in/out. */
+    sfdtd_array state_u, state_z;
+    /* string_params (simulator.cpp:17; string.cpp:68-70): kappa(B) alpha(B) p_a(B) f0(B,Nt) pos(B) T60(B,2,2 contiguous, bs = string stride) */
+    sfdtd_array kappa, alpha, p_a, f0, pos, T60;
+    /* bow_params (string.cpp:73-74): x_b v_b F_b wid (B,Nt); phi_0 phi_1 (B) */
+    sfdtd_array x_b, v_b, F_b, wid, phi_0, phi_1;
+    /* hammer_params (string.cpp:77-78): x_H w_H M_r alpha_H (B); u_H (B,Nt) updated IN PLACE: u_H[:,n] += u_H (string.cpp:303) */
+    sfdtd_array x_H, w_H, M_r, alpha_H, u_H;
+    /* excitation masks, uint8 (B) */
+    const uint8_t *bow_mask, *hammer_mask;
+    /* float32 table torch.linspace(1/Nx_t1, 1, Nx_t1) built by the host exactly as the reference does (misc.cpp:26-27) */
+    const float *xax;
+
+    /* outputs (B,Nt), columns 0 and 1 are left untouched (the caller discards them, src/task/simulate.py:82-86) */
+    sfdtd_array uout, zout, v_r, F_H, u_H_out;   /* u_H_out = u_H / k (simulator.cpp:57) */
+    /* outputs (B): loss parameters of the last step (string.cpp:119-120) */
+    void *sig0, *sig1;
+    uint32_t *status;      /* (B) status bits, may be NULL */
+    /* optional (may be NULL): per-string int64[4] counters {outer iterations, linear sweeps, hammer iterations, steps} */
+    int64_t *counters;
+} sfdtd_args;
+
+/* Runs steps 2..Nt-1 for all B strings on `cuda_stream` (a cudaStream_t, NULL = default stream).
+ * Asynchronous with respect to the host except for one small device->host read used to size the launch. */
+int sfdtd_forward(const sfdtd_args *args, void *cuda_stream);
+
+/* Human-readable description of the last error on this thread. */
+const char *sfdtd_last_error(void);
+
+/* ABI / build info */
+int sfdtd_abi_version(void);
+/* number of kernel launches issued by sfdtd_forward calls since load (for bench accounting) */
+int64_t sfdtd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFDTD_H_ */

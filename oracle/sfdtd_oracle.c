@@ -19,6 +19,7 @@
  * Each function cites the reference lines it follows.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
@@ -49,6 +50,11 @@ typedef struct {
        hammer_total, hammer_max, steps] */
     int64_t *stats;
     int32_t max_iter; /* safety cap on the (uncapped in the reference) loops */
+    /* 0: dense LU (faithful to inv+matmul).  1: matrix-free block Gauss-Seidel on the
+       t/l blocks with Thomas solves -- the algorithm of the CUDA kernel, kept here so
+       that it can be validated against the goldens on the CPU.
+       stats[5]=sweeps total, stats[6]=sweeps max, stats[7]=solves */
+    int32_t solver;
 } sfdtd_oracle_args;
 
 /* ---- per-string, per-step derived quantities --------------------------------
@@ -279,6 +285,58 @@ static double msf(double gamma, double sig0, double K, double p_a, double x, dou
     return (p_a * (cos_term + sin_term)) * exp((-1 * sigma) * t);
 }
 
+
+/* ---- matrix-free operators (solver == 1) ------------------------------------ */
+/* out = K_tl z = -phi Dxf Lam Dxb Int_tl z   (string.cpp:158) */
+static void apply_Ktl(const ws_t *w, int Wt, int Wl, double phi, const double *z, double *out, double *y)
+{
+    const int Nt_ = w->d.N_t, Nl_ = w->d.N_l; const double ht = w->d.h_t;
+    for (int i = 0; i < Wt; i++) {
+        if (i <= Nt_) {
+            int i0, i1; double l0, l1;
+            interp_row(Nl_ + 1, Nt_ + 1, i, &i0, &i1, &l0, &l1);
+            y[i] = (i0 < Wl ? l0 * z[i0] : 0.0) + (i1 < Wl ? l1 * z[i1] : 0.0);
+        } else y[i] = 0.0;
+    }
+    double qprev = 0.0; /* q_i = lam_i (y_i - y_{i-1})/ht */
+    double q0 = w->lam[0] * (y[0] / ht);
+    qprev = q0;
+    for (int i = 0; i < Wt; i++) {
+        double qn = (i + 1 < Wt) ? w->lam[i + 1] * ((y[i + 1] - y[i]) / ht) : 0.0;
+        out[i] = -phi * ((qn - qprev) / ht);
+        qprev = qn;
+    }
+}
+/* out = K_lt u = -phi Dxf_l Int_lt Lam Dxb u   (string.cpp:159) */
+static void apply_Klt(const ws_t *w, int Wt, int Wl, double phi, const double *u, double *out, double *q)
+{
+    const int Nt_ = w->d.N_t, Nl_ = w->d.N_l; const double ht = w->d.h_t, hl = w->d.h_l;
+    for (int i = 0; i < Wt; i++) q[i] = w->lam[i] * ((u[i] - (i > 0 ? u[i - 1] : 0.0)) / ht);
+    double pprev = 0.0;
+    for (int j = 0; j <= Wl; j++) {
+        double p = 0.0;
+        if (j < Wl && j <= Nl_) {
+            int i0, i1; double l0, l1;
+            interp_row(Nt_ + 1, Nl_ + 1, j, &i0, &i1, &l0, &l1);
+            p = (i0 < Wt ? l0 * q[i0] : 0.0) + (i1 < Wt ? l1 * q[i1] : 0.0);
+        }
+        if (j > 0) out[j - 1] = -phi * ((p - pprev) / hl);
+        pprev = p;
+    }
+}
+/* Thomas solve, tridiagonal (a sub, b diag, c super), cp = scratch */
+static void thomas(const double *a, const double *b, const double *c, double *d, double *cp, int n)
+{
+    double den = b[0];
+    cp[0] = c[0] / den; d[0] = d[0] / den;
+    for (int i = 1; i < n; i++) {
+        den = b[i] - a[i] * cp[i - 1];
+        cp[i] = c[i] / den;
+        d[i] = (d[i] - a[i] * d[i - 1]) / den;
+    }
+    for (int i = n - 2; i >= 0; i--) d[i] -= cp[i] * d[i + 1];
+}
+
 int sfdtd_oracle_forward(sfdtd_oracle_args *a)
 {
     const int B = a->B, Nt = a->Nt, NXT = a->Nx_t1, NXL = a->Nx_l1;
@@ -303,9 +361,9 @@ int sfdtd_oracle_forward(sfdtd_oracle_args *a)
         w->Ktl = dalloc((size_t)NXT * NXL); w->Klt = dalloc((size_t)NXT * NXL);
         w->rb = dalloc(NTOT); w->rhs = dalloc(NTOT);
         w->u = dalloc(NXT); w->z = dalloc(NXL); w->unew = dalloc(NXT); w->znew = dalloc(NXL);
-        w->rc = dalloc(NXT); w->tmp = dalloc(NTOT); w->tmp2 = dalloc((size_t)NTOT * NTOT);
+        w->rc = dalloc(NXT); w->tmp = dalloc(NTOT); w->tmp2 = dalloc((size_t)NTOT * NTOT + 16 * (size_t)NTOT + 64);
     }
-    if (a->stats) memset(a->stats, 0, 5 * sizeof(int64_t));
+    if (a->stats) memset(a->stats, 0, 8 * sizeof(int64_t));
 
     for (int n = 2; n < Nt; n++) {                        /* simulator.cpp:40 */
         /* ---- derived vars, group-max operator widths (misc.cpp:119-127) ---- */
@@ -502,9 +560,56 @@ int sfdtd_oracle_forward(sfdtd_oracle_args *a)
                 for (int i = 0; i < Wt; i++) if (!(i < keep)) w->rhs[i] *= 0.0;
                 for (int j = 0; j < Wl; j++) if (!(NXT + j < keep)) w->rhs[Wt + j] *= 0.0;
                 /* solve A w = -RHS */
-                memcpy(w->tmp2, w->A, (size_t)nw * nw * sizeof(double));
-                for (int i = 0; i < nw; i++) w->tmp[i] = -w->rhs[i];
-                lu_solve(w->tmp2, w->tmp, nw);
+                if (a->solver == 0) {
+                    memcpy(w->tmp2, w->A, (size_t)nw * nw * sizeof(double));
+                    for (int i = 0; i < nw; i++) w->tmp[i] = -w->rhs[i];
+                    lu_solve(w->tmp2, w->tmp, nw);
+                } else {
+                    /* block Gauss-Seidel: A11 u = -r_t - K_tl z ;  A22 z = -r_l - K_lt u */
+                    const double g_ = (d->gamma * d->gamma) * k2;
+                    const double phi_ = (g_ * (a->alpha[b] * a->alpha[b] - 1)) / 4;
+                    double *ta = w->tmp2, *tb = ta + nw, *tc = tb + nw, *cp = tc + nw,
+                           *la = cp + nw, *lb = la + nw, *lc = lb + nw, *sc1 = lc + nw, *sc2 = sc1 + nw + 2,
+                           *uu = sc2 + nw + 2, *zz = uu + nw, *uo = zz + nw, *zo = uo + nw;
+                    for (int i = 0; i < Wt; i++) {
+                        ta[i] = (i > 0) ? w->A[(size_t)i * nw + i - 1] : 0.0;
+                        tb[i] = w->A[(size_t)i * nw + i];
+                        tc[i] = (i + 1 < Wt) ? w->A[(size_t)i * nw + i + 1] : 0.0;
+                    }
+                    for (int j = 0; j < Wl; j++) {
+                        la[j] = (j > 0) ? w->A[(size_t)(Wt + j) * nw + Wt + j - 1] : 0.0;
+                        lb[j] = w->A[(size_t)(Wt + j) * nw + Wt + j];
+                        lc[j] = (j + 1 < Wl) ? w->A[(size_t)(Wt + j) * nw + Wt + j + 1] : 0.0;
+                    }
+                    const double GS_TOL = getenv("SFDTD_GSTOL") ? atof(getenv("SFDTD_GSTOL")) : 1e-13;
+                    const int guess = getenv("SFDTD_GUESS") ? atoi(getenv("SFDTD_GUESS")) : 0;
+                    for (int j = 0; j < Wl; j++) zz[j] = guess == 0 ? 0.0 : (guess == 1 ? w->z1[j] : 2 * w->z1[j] - w->z2[j]);
+                    for (int i = 0; i < Wt; i++) uu[i] = 0.0;
+                    int sweeps = 0;
+                    for (;;) {
+                        for (int i = 0; i < Wt; i++) uo[i] = uu[i];
+                        for (int j = 0; j < Wl; j++) zo[j] = zz[j];
+                        if (phi_ != 0.0) apply_Ktl(w, Wt, Wl, phi_, zz, uu, sc1);
+                        else for (int i = 0; i < Wt; i++) uu[i] = 0.0;
+                        for (int i = 0; i < Wt; i++) uu[i] = -w->rhs[i] - uu[i];
+                        thomas(ta, tb, tc, uu, cp, Wt);
+                        if (phi_ != 0.0) apply_Klt(w, Wt, Wl, phi_, uu, zz, sc1);
+                        else for (int j = 0; j < Wl; j++) zz[j] = 0.0;
+                        for (int j = 0; j < Wl; j++) zz[j] = -w->rhs[Wt + j] - zz[j];
+                        thomas(la, lb, lc, zz, cp, Wl);
+                        sweeps++;
+                        double du = 0, su_ = 0, dz = 0, sz_ = 0;
+                        for (int i = 0; i < Wt; i++) { double e = fabs(uu[i] - uo[i]); if (e > du) du = e; e = fabs(uu[i]); if (e > su_) su_ = e; }
+                        for (int j = 0; j < Wl; j++) { double e = fabs(zz[j] - zo[j]); if (e > dz) dz = e; e = fabs(zz[j]); if (e > sz_) sz_ = e; }
+                        if (!(du > GS_TOL * su_) && !(dz > GS_TOL * sz_)) break;   /* also exits on NaN */
+                        if (getenv("SFDTD_DEBUG") && sweeps >= 20 && sweeps < 24)
+                            fprintf(stderr, "n=%d b=%d it=%d sweep=%d du=%.3e su=%.3e dz=%.3e sz=%.3e\n", n, b, iter, sweeps, du, su_, dz, sz_);
+                        if (sweeps >= 500) { status = 2; break; }
+                    }
+                    if (a->stats) { a->stats[5] += sweeps; if (sweeps > a->stats[6]) a->stats[6] = sweeps; a->stats[7] += 1; }
+                    for (int i = 0; i < Wt; i++) w->tmp[i] = uu[i];
+                    for (int j = 0; j < Wl; j++) w->tmp[Wt + j] = zz[j];
+                }
                 /* mask + Dirichlet (string.cpp:240-246) */
                 double res_u = 0, res_z = 0; int nanu = 0, nanz = 0;
                 for (int i = 0; i < NXT; i++) {

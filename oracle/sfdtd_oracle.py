@@ -39,7 +39,7 @@ class _Args(ctypes.Structure):
         ("relative_order", ctypes.c_float),
         ("surface_integral", ctypes.c_int32), ("manufactured", ctypes.c_int32), ("n_0", ctypes.c_int32),
         ("uout", _P), ("zout", _P), ("v_r", _P), ("F_H", _P), ("u_H_out", _P), ("sig0", _P), ("sig1", _P),
-        ("stats", _P), ("max_iter", ctypes.c_int32),
+        ("stats", _P), ("max_iter", ctypes.c_int32), ("solver", ctypes.c_int32),
     ]
 
 
@@ -68,7 +68,7 @@ last_stats = None
 
 def forward_fn(state_u, state_z, string_params, bow_params, hammer_params,
                bow_mask, hammer_mask, constant, relative_error,
-               surface_integral, manufactured, n_0, Nt, max_iter=1000):
+               surface_integral, manufactured, n_0, Nt, max_iter=1000, solver=0):
     """Drop-in for the reference ``forward_fn`` (simulator.cpp:14-27). fp64 only."""
     global last_stats
     lib = _get_lib()
@@ -90,7 +90,7 @@ def forward_fn(state_u, state_z, string_params, bow_params, hammer_params,
 
     outs = {n: torch.zeros(B, Nt, dtype=torch.float64) for n in ["uout", "zout", "v_r", "F_H", "u_H_out"]}
     sig0 = torch.zeros(B, dtype=torch.float64); sig1 = torch.zeros(B, dtype=torch.float64)
-    stats = np.zeros(5, dtype=np.int64)
+    stats = np.zeros(8, dtype=np.int64)
     a = _Args()
     a.B, a.Nt, a.Nx_t1, a.Nx_l1 = B, Nt, Nx_t1, Nx_l1
     a.state_u, a.state_z = su.data_ptr(), sz.data_ptr()
@@ -110,11 +110,13 @@ def forward_fn(state_u, state_z, string_params, bow_params, hammer_params,
     a.sig0, a.sig1 = sig0.data_ptr(), sig1.data_ptr()
     a.stats = stats.ctypes.data
     a.max_iter = max_iter
+    a.solver = solver
     rc = lib.sfdtd_oracle_forward(ctypes.byref(a))
     if rc < 0:
         raise RuntimeError(f"sfdtd_oracle_forward failed with status {rc}")
     last_stats = dict(outer_total=int(stats[0]), outer_max=int(stats[1]), hammer_total=int(stats[2]),
-                      hammer_max=int(stats[3]), steps=int(stats[4]), capped=(rc == 1))
+                      hammer_max=int(stats[3]), steps=int(stats[4]), capped=(rc == 1),
+                      gs_sweeps=int(stats[5]), gs_sweeps_max=int(stats[6]), gs_solves=int(stats[7]))
     # in-place side effects of the reference (string.cpp:264-265,303)
     if su.data_ptr() != state_u.data_ptr():
         state_u.copy_(su.to(state_u.dtype))

@@ -1,0 +1,11 @@
+"""B200-native drop-in for StringFDTD-Torch's batched time stepper.
+
+Public surface (mirrors the reference for this path only):
+  forward_fn(...)            -- reference src/model/cpp/simulator.cpp:14-27 (the pybind entry point)
+  process(...)               -- reference src/task/simulate.py:16-119 (the chunk driver)
+  step_strings(...)          -- native compact-input API (no (B,Nt,Nx) tensors)
+"""
+from .forward_fn import forward_fn, step_strings, make_xax, launch_count  # noqa: F401
+from .simulate import process  # noqa: F401
+
+__all__ = ["forward_fn", "process", "step_strings", "make_xax", "launch_count"]

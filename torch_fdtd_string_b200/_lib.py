@@ -1,0 +1,59 @@
+"""ctypes binding of libsfdtd.so (include/sfdtd.h).  There is NO fallback: if the CUDA
+library is missing or fails to load, importing the stepper raises."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsfdtd.so")
+
+SFDTD_ABI_VERSION = 1
+SFDTD_F64 = 0
+SURFACE_INTEGRAL, MANUFACTURED, SAVE_STATE, SKIP_AUX = 1, 2, 4, 8
+ST_SOLVER_CAP, ST_OUTER_CAP, ST_HAMMER_CAP, ST_BOW_WINDOW, ST_RANGE = 1, 2, 4, 8, 16
+
+EXPORTS = ["sfdtd_forward", "sfdtd_last_error", "sfdtd_abi_version", "sfdtd_launch_count"]
+
+
+class Array(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("bs", ctypes.c_int64), ("ts", ctypes.c_int64)]
+
+
+class Args(ctypes.Structure):
+    _fields_ = (
+        [("abi_version", ctypes.c_int32), ("dtype", ctypes.c_int32), ("flags", ctypes.c_uint32),
+         ("B", ctypes.c_int32), ("group_size", ctypes.c_int32), ("Nt", ctypes.c_int32),
+         ("Nx_t1", ctypes.c_int32), ("Nx_l1", ctypes.c_int32), ("n_0", ctypes.c_int32),
+         ("max_iter", ctypes.c_int32),
+         ("k", ctypes.c_float), ("theta_t", ctypes.c_float), ("lambda_c", ctypes.c_float),
+         ("relative_order", ctypes.c_float)]
+        + [(n, Array) for n in ("state_u", "state_z", "kappa", "alpha", "p_a", "f0", "pos", "T60",
+                                "x_b", "v_b", "F_b", "wid", "phi_0", "phi_1",
+                                "x_H", "w_H", "M_r", "alpha_H", "u_H")]
+        + [("bow_mask", ctypes.c_void_p), ("hammer_mask", ctypes.c_void_p), ("xax", ctypes.c_void_p)]
+        + [(n, Array) for n in ("uout", "zout", "v_r", "F_H", "u_H_out")]
+        + [("sig0", ctypes.c_void_p), ("sig1", ctypes.c_void_p), ("status", ctypes.c_void_p),
+           ("counters", ctypes.c_void_p)]
+    )
+
+
+_lib = None
+
+
+def load():
+    """Loads libsfdtd.so; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m torch_fdtd_string_b200.build` "
+                "(there is no CPU or PyTorch fallback for the stepper)")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.sfdtd_forward.argtypes = [ctypes.POINTER(Args), ctypes.c_void_p]
+        lib.sfdtd_forward.restype = ctypes.c_int
+        lib.sfdtd_last_error.restype = ctypes.c_char_p
+        lib.sfdtd_abi_version.restype = ctypes.c_int
+        lib.sfdtd_launch_count.restype = ctypes.c_int64
+        if lib.sfdtd_abi_version() != SFDTD_ABI_VERSION:
+            raise RuntimeError("libsfdtd.so ABI version mismatch")
+        _lib = lib
+    return _lib
