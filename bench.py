@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched StringFDTD time stepper (BASELINE.json metric:
+simulated string-seconds/sec and grid-point-updates/sec at 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, host cores
+
+One "step" = one pass of the hot path over one batch: `--strings` nsynth-like strings (groups of 24
+= the reference's batch_size, experiment=nsynth-like), every string simulated for `--length` seconds
+at 48 kHz in fp64.  N>1: one process per GPU (torchrun), the batch of independent groups is sharded,
+no collective on the data path (weak scaling: per-GPU work fixed).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 48000
+GROUP = 24                      # task.batch_size of experiment=nsynth-like
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--strings", type=int, default=148 * GROUP, help="strings per GPU (multiple of 24)")
+    ap.add_argument("--length", type=float, default=1.0, help="seconds of audio per string")
+    ap.add_argument("--excitation", default="pluck")
+    ap.add_argument("--skip-aux", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-nt", type=int, default=26, help="samples per reference-arm step (bounded sample)")
+    ap.add_argument("--p-a-max", type=float, default=None, help="override the pluck amplitude cap (diagnostics only)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons of one GPU during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def reference_arm(a, rank):
+    """times the reference's own CPU implementation (oracle/_ref, else the C port) on the host cores"""
+    if rank != 0:
+        return
+    Nt_s = a.ref_nt
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--B", str(GROUP), "--nt", str(Nt_s),
+           "--steps", str(a.steps), "--warmup", str(a.warmup), "--excitation", a.excitation]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=3000)
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    if not line:
+        print(json.dumps({"impl": "reference", "unavailable": (out.stderr.strip().splitlines() or ["no output"])[-1][:200]}))
+        return
+    r = json.loads(line[-1])
+    t = sum(r["sec_per_call"]) / len(r["sec_per_call"])
+    val = GROUP * (Nt_s - 2) / SR / t
+    sample = (f"{GROUP} nsynth-like {a.excitation} strings (one reference batch), first {Nt_s - 2} of 47998 steps per "
+              f"step, fp64, {r['cores']} host threads; steps are homogeneous so the rate extrapolates linearly")
+    print(json.dumps({
+        "impl": "reference", "metric": "simulated string-seconds/sec", "value": val, "unit": "string-seconds/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, a.strings),
+        "cpu_baseline": {"value": val, "unit": "string-seconds/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
+        "e2e": {"value": val, "unit": "string-seconds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(a, strings):
+    return {"workload": f"nsynth-like dataset generation ({a.excitation}), {strings} strings/GPU in reference batches "
+                        f"of {GROUP}, {a.length:g} s @ 48 kHz, random string params (experiment=nsynth-like ranges)",
+            "strings_per_gpu": strings, "group_size": GROUP, "sr": SR, "length_s": a.length,
+            "excitation": a.excitation, "precision": "double", "aux_outputs": "skipped" if a.skip_aux else "reference-faithful",
+            "l2": "inputs larger than L2 (f0 + outputs >> 126 MB), no flush needed"}
+
+
+def algorithmic_work(p, ctl, counters, group):
+    """F_step = 60 W_t + 30 W_l + S (110 W_t + 74 W_l) + I (4 (W_t + W_l) + 50) per string-step,
+    W = batch-max operator widths of the step; grid-point updates = N_t+1 + N_l+1 per string-step."""
+    import numpy as np
+    import torch
+    k = float(np.float32(p["k"])); th = float(np.float32(p["theta_t"])); lam = float(np.float32(p["lambda_c"]))
+    tt1 = float(np.float32(2 * np.float32(th) - 1)); tt2 = float(np.float32(2 * np.float32(tt1)))
+    f0 = ctl["f0"][:, 2:]
+    B = f0.size(0)
+    gamma = 2 * f0
+    K = gamma * p["kappa"].view(-1, 1)
+    h1 = lam * ((gamma ** 2 * k ** 2 + (gamma ** 4 * k ** 4 + 16 * K ** 2 * k ** 2 * tt1).sqrt()) / tt2).sqrt()
+    Nt_ = (1 / h1).floor()
+    Nl_ = (1 / (lam * gamma * p["alpha"].view(-1, 1) * k)).floor()
+    gpu_updates = float((Nt_ + 1 + Nl_ + 1).sum())
+    G = B // group
+    Wt = (Nt_.view(G, group, -1).max(dim=1).values + 1)
+    Wl = (Nl_.view(G, group, -1).max(dim=1).values + 1)
+    S = (1 + p["bow_mask"].double() + p["hammer_mask"].double()).view(G, group, 1)
+    I = (counters[:, 0].double() / counters[:, 3].clamp(min=1).double()).view(G, group, 1)
+    Wt_ = Wt.unsqueeze(1); Wl_ = Wl.unsqueeze(1)
+    F = (60 * Wt_ + 30 * Wl_) + S * (110 * Wt_ + 74 * Wl_) + I * (4 * (Wt_ + Wl_) + 50)
+    # bytes: 6 control reads + 5 output writes per string-step (fp64) + initial rows
+    bytes_ = B * f0.size(1) * 11 * 8 + B * 2 * (p["Nx_t1"] + p["Nx_l1"]) * 8
+    return float(F.sum()), gpu_updates, float(bytes_), float(Wt.mean()), float(Wl.mean())
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        reference_arm(a, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    from torch_fdtd_string_b200 import _lib, launch_count
+    from torch_fdtd_string_b200 import sampler
+    from torch_fdtd_string_b200.forward_fn import step_strings
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    B = (a.strings // GROUP) * GROUP
+    p_host = sampler.sample_nsynth_like(B, sr=SR, length=a.length, excitation=a.excitation, seed=1234 + rank,
+                                        cfg=(dict(p_a_max=a.p_a_max) if a.p_a_max else None))
+    Nt = p_host["Nt"]
+    p = sampler.to_device(p_host, dev)
+    ctl = sampler.expand_controls(p, dev)
+    f64 = dict(dtype=torch.float64, device=dev)
+    out = {n: torch.zeros(B, Nt, **f64) for n in ("uout", "zout", "v_r", "F_H", "u_H_out")}
+
+    def one_step(counters=False):
+        su = p["state_u"].clone(); sz = p["state_z"].clone()
+        uH = ctl["u_H"].clone()
+        return step_strings(
+            su, sz, kappa=p["kappa"], alpha=p["alpha"], f0=ctl["f0"], pos=p["pos"], T60=p["T60"],
+            x_b=ctl["x_b"], v_b=ctl["v_b"], F_b=ctl["F_b"], wid=ctl["wid"], phi_0=p["phi_0"], phi_1=p["phi_1"],
+            x_H=p["x_H"], w_H=p["w_H"], M_r=p["M_r"], alpha_H=p["alpha_H"], u_H=uH,
+            bow_mask=p["bow_mask"], hammer_mask=p["hammer_mask"], k=p["k"], theta_t=p["theta_t"],
+            lambda_c=p["lambda_c"], relative_order=p["relative_order"], Nt=Nt, group_size=GROUP,
+            surface_integral=True, save_state=False, skip_aux=a.skip_aux, p_a=p["p_a"], out=out,
+            counters=counters, check=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    res = None
+    for _ in range(max(a.warmup, 1)):
+        res = one_step(counters=True)
+    status = int(res["status"].max())
+    counters = res["counters"]
+    nan_strings = int(torch.isnan(out["uout"][:, 2:]).any(dim=1).sum())
+
+    # ---- timed region: K steps, CUDA events on the launching stream, max over ranks ----
+    clocks = ClockSampler(local_rank); clocks.start()
+    l0 = launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        one_step()
+    e1.record()
+    barrier()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    launches = launch_count() - l0
+    clk = clocks.stop()
+    tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_max = float(tt)
+    per_step = t_max / a.steps
+    string_seconds = world * B * (Nt - 2) / SR
+    value = string_seconds / per_step
+
+    flops, gpu_upd, bytes_, Wt_mean, Wl_mean = algorithmic_work(p, ctl, counters, GROUP)
+
+    # ---- end-to-end through the public API with host buffers (H2D of the compact parameters, D2H of the audio) ----
+    e2e = None
+    if not a.no_e2e:
+        pin = {kx: p_host[kx].pin_memory() for kx in sampler.TENSOR_KEYS}
+        ph = dict(p_host); ph.update(pin)
+        h_u = torch.empty(B, Nt - 2, dtype=torch.float64).pin_memory()
+        h_z = torch.empty(B, Nt - 2, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            q = sampler.to_device(ph, dev, non_blocking=True)
+            r = sampler.run_compact(q, GROUP, skip_aux=a.skip_aux)
+            h_u.copy_(r["uout"][:, 2:], non_blocking=True)
+            h_z.copy_(r["zout"][:, 2:], non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(a.steps, 3))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": string_seconds / float(te), "unit": "string-seconds/s",
+               "h2d_bytes_per_step": sampler.compact_nbytes(p_host), "d2h_bytes_per_step": 2 * B * (Nt - 2) * 8,
+               "ms_per_step": float(te) * 1e3,
+               "note": "pinned host compact parameters -> H2D -> on-device control expansion -> stepper -> D2H of uout,zout"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: FP64 FMA pipe (measured on this GPU), HBM as the secondary line ----
+    import ctypes
+    peak = ctypes.c_double(0.0)
+    peak_src = "measured (sfdtd_measure_fma_peak: register-resident DFMA chains, this GPU, this run)"
+    if lib.sfdtd_measure_fma_peak(0, ctypes.byref(peak)) != 0 or peak.value <= 0:
+        peak.value = 37.2; peak_src = "nominal 148 SM x 64 lanes x 2 x 1.965 GHz"
+    achieved = flops / per_step / 1e12
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]; hbm_src = "of measured (MEASURED_PEAKS.json)"
+    except Exception:
+        hbm_peak = 6650.0; hbm_src = "of fallback"
+    roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
+                "traffic": None, "peak_source": peak_src, "peak_nominal": 37.2, "frac_of_nominal": achieved / 37.2,
+                "flops_per_string_step": flops / (B * (Nt - 2)),
+                "note": "algorithmic flops per SURVEY.md 8(d) / CUDA-event time of the stepping launch; tensor cores unused (no dense contraction)"}
+    roofline_hbm = {"bound": "hbm", "achieved": bytes_ / per_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": bytes_ / per_step / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        try:
+            o = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--B", str(GROUP), "--nt", "62",
+                                "--steps", "1", "--warmup", "0", "--excitation", a.excitation],
+                               capture_output=True, text=True, timeout=1200)
+            r = json.loads([l for l in o.stdout.splitlines() if l.startswith("{")][-1])
+            t = r["sec_per_call"][0]
+            cpu = {"value": GROUP * 60 / SR / t, "unit": "string-seconds/s", "cores": r["cores"], "kind": r["kind"],
+                   "sample": f"one reference batch ({GROUP} strings) x 60 steps, fp64, {r['cores']} host threads "
+                             f"({r['host_cpus']} cpus), {t:.1f} s wall; steps homogeneous, rate extrapolates linearly"}
+        except Exception as e:
+            cpu = {"value": None, "unit": "string-seconds/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+
+    print(json.dumps({
+        "metric": "simulated string-seconds/sec", "value": value, "unit": "string-seconds/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, B),
+        "grid_point_updates_per_s": world * gpu_upd / per_step,
+        "mean_operator_widths": {"W_t": Wt_mean, "W_l": Wl_mean},
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clk,
+        "health": {"status_bits": status, "nan_strings": nan_strings,
+                   "mean_outer_iters": float(counters[:, 0].sum()) / max(1.0, float(counters[:, 3].sum())),
+                   "mean_sweeps_per_step": float(counters[:, 1].sum()) / max(1.0, float(counters[:, 3].sum())),
+                   "per_string_mean_sweeps_p50_p99_max": [float(x) for x in torch.quantile(
+                       counters[:, 1].double() / counters[:, 3].clamp(min=1).double(),
+                       torch.tensor([0.5, 0.99, 1.0], dtype=torch.float64, device=dev))]},
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -112,6 +112,10 @@ int sfdtd_forward(const sfdtd_args *args, void *cuda_stream);
 /* Human-readable description of the last error on this thread. */
 const char *sfdtd_last_error(void);
 
+/* FMA-pipe peak of the current device in TFLOP/s (2 flops per FMA), measured with a register-resident
+ * FMA-chain kernel: which = 0 -> fp64, 1 -> fp32.  Roofline denominator for bench.py. */
+int sfdtd_measure_fma_peak(int which, double *tflops);
+
 /* ABI / build info */
 int sfdtd_abi_version(void);
 /* number of kernel launches issued by sfdtd_forward calls since load (for bench accounting) */

@@ -11,7 +11,8 @@ SFDTD_F64 = 0
 SURFACE_INTEGRAL, MANUFACTURED, SAVE_STATE, SKIP_AUX = 1, 2, 4, 8
 ST_SOLVER_CAP, ST_OUTER_CAP, ST_HAMMER_CAP, ST_BOW_WINDOW, ST_RANGE = 1, 2, 4, 8, 16
 
-EXPORTS = ["sfdtd_forward", "sfdtd_last_error", "sfdtd_abi_version", "sfdtd_launch_count"]
+EXPORTS = ["sfdtd_forward", "sfdtd_last_error", "sfdtd_abi_version", "sfdtd_launch_count",
+           "sfdtd_measure_fma_peak"]
 
 
 class Array(ctypes.Structure):
@@ -53,6 +54,8 @@ def load():
         lib.sfdtd_last_error.restype = ctypes.c_char_p
         lib.sfdtd_abi_version.restype = ctypes.c_int
         lib.sfdtd_launch_count.restype = ctypes.c_int64
+        lib.sfdtd_measure_fma_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        lib.sfdtd_measure_fma_peak.restype = ctypes.c_int
         if lib.sfdtd_abi_version() != SFDTD_ABI_VERSION:
             raise RuntimeError("libsfdtd.so ABI version mismatch")
         _lib = lib

@@ -803,6 +803,22 @@ __global__ void __launch_bounds__(MAXT, 1) sfdtd_step_kernel(const __grid_consta
     }
 }
 
+// ---- FMA-pipe peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has no FP64/FP32 FMA figure) ----
+template <typename T>
+__global__ void __launch_bounds__(256) sfdtd_fma_peak_kernel(T *out, int iters, T seed) {
+    T a0 = seed + (T)threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const T m = (T)0.999999, c = (T)1e-9;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+            a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+        }
+    }
+    const T r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == (T)-1) out[0] = r;     // never true: keeps the chains alive
+}
+
 // ======================================================================================================
 // host side
 // ======================================================================================================
@@ -834,6 +850,36 @@ size_t smem_bytes(const Config &c, int nslots, int NXT, size_t lblk_doubles) {
 extern "C" const char *sfdtd_last_error(void) { return g_err; }
 extern "C" int sfdtd_abi_version(void) { return SFDTD_ABI_VERSION; }
 extern "C" int64_t sfdtd_launch_count(void) { return g_launches.load(); }
+
+// Measures the achievable FMA-pipe rate (TFLOP/s, 2 flops per FMA) of the current device: which = 0 fp64, 1 fp32.
+extern "C" int sfdtd_measure_fma_peak(int which, double *tflops) {
+    g_err[0] = 0;
+    if (!tflops) return SFDTD_ERR_ARG;
+    int rc = SFDTD_OK, dev = 0, sms = 0;
+    void *buf = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float ms = 0, best = 1e30f;
+    const int iters = which == 0 ? 4096 : 8192, blocks_per_sm = 8;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaMalloc(&buf, 64));
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 6; rep++) {
+        CK(cudaEventRecord(e0));
+        if (which == 0) sfdtd_fma_peak_kernel<double><<<sms * blocks_per_sm, 256>>>((double *)buf, iters, 1.0);
+        else sfdtd_fma_peak_kernel<float><<<sms * blocks_per_sm, 256>>>((float *)buf, iters, 1.0f);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *tflops = 2.0 * 64.0 * iters * 256.0 * sms * blocks_per_sm / (best * 1e-3) / 1e12;
+done:
+    if (buf) cudaFree(buf);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
+}
 
 extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     g_err[0] = 0;
