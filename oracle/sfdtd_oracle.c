@@ -564,6 +564,77 @@ int sfdtd_oracle_forward(sfdtd_oracle_args *a)
                     memcpy(w->tmp2, w->A, (size_t)nw * nw * sizeof(double));
                     for (int i = 0; i < nw; i++) w->tmp[i] = -w->rhs[i];
                     lu_solve(w->tmp2, w->tmp, nw);
+                } else if (a->solver == 2) {
+                    /* CPU prototype of the CUDA kernel's solve (DESIGN.md "linear solve"):
+                     *  - transverse rows trimmed to R = min(W_t, max(N_t+3, last forced row+1)); the homogeneous
+                     *    Toeplitz ghost tail R..W_t-1 is folded exactly into the pivot of row R-1 (continued fraction);
+                     *  - longitudinal rows trimmed to min(N_l+3, W_l), A22 by Jacobi sweeps folded into the block iteration;
+                     *  - initial coupling guess z = 2 z1 - z2; rate-based stopping rule on the predicted error. */
+                    const double g_ = (d->gamma * d->gamma) * k2;
+                    const double phi_ = (g_ * (a->alpha[b] * a->alpha[b] - 1)) / 4;
+                    double *ta = w->tmp2, *tb = ta + nw, *tc = tb + nw, *cp = tc + nw,
+                           *sc1 = cp + nw, *uu = sc1 + nw + 2, *zc = uu + nw, *zn = zc + nw, *uo = zn + nw, *kz = uo + nw, *kl = kz + nw;
+                    int last = -1;
+                    for (int i = 0; i < Wt; i++) if (w->rhs[i] != 0.0) last = i;
+                    int R = N_t + 3; if (last + 1 > R) R = last + 1; if (R > Wt) R = Wt;
+                    const double offA = w->A[(size_t)(Wt - 1) * nw + Wt - 2];   /* Toeplitz tail coefficients */
+                    const double diagA = (Wt - 1 >= N_t + 2) ? w->A[(size_t)(Wt - 1) * nw + Wt - 1] : 0.0;
+                    for (int i = 0; i < R; i++) {
+                        ta[i] = (i > 0) ? w->A[(size_t)i * nw + i - 1] : 0.0;
+                        tb[i] = w->A[(size_t)i * nw + i];
+                        tc[i] = (i + 1 < R) ? w->A[(size_t)i * nw + i + 1] : 0.0;
+                    }
+                    if (Wt > R) {
+                        const int m = Wt - R;
+                        double pv = diagA;
+                        for (int j = 1; j < m; j++) { double pn = diagA - (offA * offA) / pv; if (pn == pv) break; pv = pn; }
+                        tb[R - 1] -= (offA * offA) / pv;
+                    }
+                    int WLs = N_l + 3; if (WLs > Wl) WLs = Wl;
+                    const double dA = w->A[(size_t)(Wt) * nw + Wt], eA = (Wl > 1) ? w->A[(size_t)(Wt) * nw + Wt + 1] : 0.0;
+                    for (int j = 0; j < Wl; j++) { zc[j] = w->z1[j]; zn[j] = 0.0; }
+                    for (int i = 0; i < Wt; i++) uu[i] = 0.0;
+                    for (int j = 0; j < Wl; j++) kl[j] = 2 * w->z1[j] - w->z2[j];
+                    int sweeps = 0; double du_prev = 0, su_ = 0;
+                    const double TOL = getenv("SFDTD_TOL2") ? atof(getenv("SFDTD_TOL2")) : 1e-13;
+                    static __thread double rho_hist[4096];
+                    double rho_h = (n == 2) ? 0.5 : rho_hist[b & 4095];
+                    for (;;) {
+                        for (int i = 0; i < R; i++) uo[i] = uu[i];
+                        if (phi_ != 0.0) apply_Ktl(w, Wt, Wl, phi_, sweeps == 0 ? kl : zc, kz, sc1);
+                        else for (int i = 0; i < Wt; i++) kz[i] = 0.0;
+                        for (int i = 0; i < R; i++) uu[i] = -w->rhs[i] - kz[i];
+                        thomas(ta, tb, tc, uu, cp, R);
+                        for (int i = R; i < Wt; i++) uu[i] = 0.0;
+                        if (phi_ != 0.0) apply_Klt(w, Wt, Wl, phi_, uu, kl, sc1);
+                        else for (int j = 0; j < Wl; j++) kl[j] = 0.0;
+                        for (int j = 0; j < WLs; j++) {
+                            const double zl = j > 0 ? zc[j - 1] : 0.0, zr = (j + 1 < WLs) ? zc[j + 1] : 0.0;
+                            zn[j] = ((-w->rhs[Wt + j] - kl[j]) - eA * (zl + zr)) / dA;
+                        }
+                        for (int j = WLs; j < Wl; j++) zn[j] = 0.0;
+                        { double *t_ = zc; zc = zn; zn = t_; }
+                        sweeps++;
+                        double du = 0;
+                        for (int i = 0; i < R; i++) { double e = fabs(uu[i] - uo[i]); if (e > du || e != e) du = e; }
+                        if (sweeps == 1) for (int i = 0; i < R; i++) { double e = fabs(uu[i]); if (e > su_) su_ = e; }
+                        const int has_rl = (N_t + N_l + 2 - NXT) > 0;
+                        const int minS = has_rl ? 4 : (phi_ != 0.0 ? 2 : 1);
+                        double rho = rho_h * 2;
+                        if (sweeps >= 3 && du_prev > 0) { double r_ = du / du_prev; if (r_ > rho_h) rho_h = r_; else rho_h = 0.5 * (rho_h + r_); rho = 1.5 * rho_h; }
+                        if (rho > 0.9) rho = 0.9;
+                        const double est = du * rho / (1 - rho);
+                        du_prev = du;
+                        double dz = 0, sz_ = 0;
+                        for (int j = 0; j < WLs; j++) { double e = fabs(zc[j] - zn[j]); if (e > dz) dz = e; e = fabs(zc[j]); if (e > sz_) sz_ = e; }
+                        const double estz = dz * rho / (1 - rho);
+                        if (sweeps >= minS && !(est > TOL * su_) && !(estz > TOL * sz_)) break;      /* also exits on NaN */
+                        if (sweeps >= 500) { status = 2; break; }
+                    }
+                    rho_hist[b & 4095] = rho_h;
+                    if (a->stats) { a->stats[5] += sweeps; if (sweeps > a->stats[6]) a->stats[6] = sweeps; a->stats[7] += 1; }
+                    for (int i = 0; i < Wt; i++) w->tmp[i] = uu[i];
+                    for (int j = 0; j < Wl; j++) w->tmp[Wt + j] = zc[j];
                 } else {
                     /* block Gauss-Seidel: A11 u = -r_t - K_tl z ;  A22 z = -r_l - K_lt u */
                     const double g_ = (d->gamma * d->gamma) * k2;

@@ -1,23 +1,35 @@
 // sfdtd.cu -- B200 (sm_100a) time-loop-fused StringFDTD stepper behind the C ABI of include/sfdtd.h.
 //
-// One CTA owns one "group" (= one reference batch: the strings that share the batch-max operator
-// widths, reference misc.cpp:119-127, and the any-over-batch convergence votes, string.cpp:252-253,
-// hammer.cpp:51).  Inside the CTA every string is owned by L lanes of a warp for the whole run:
-//   * transverse block: blocked layout, ET consecutive grid rows per lane, u^{n-1}, u^{n-2} and all
-//     per-step vectors live in registers; stencil halos move with warp shuffles;
-//   * the implicit system  [A11 K_tl; K_lt A22] w = -RHS  (string.cpp:162-181,238) is solved
-//     matrix-free: block Gauss-Seidel over the transverse/longitudinal blocks; A11 (tridiagonal, varies
-//     with Lambda(u^{n-1})) by a register-resident partitioned Thomas factorisation (local LU of the
-//     ET-1 interior rows per lane + parallel cyclic reduction over the L interface rows via shuffles);
-//     A22 (constant-coefficient, off/diag ~1e-5) by Jacobi sweeps folded into the same iteration;
-//   * longitudinal block: shared memory, rows distributed cyclically over the string's lanes; the
-//     linear interpolation operators Int_tl / Int_lt (misc.cpp:78-105) are gathers from shared memory;
-//   * per-step scalars (grid sizes, loss, tolerances; string.cpp:16-41,96-120) are computed L steps at
-//     a time, one time step per lane, into a shared-memory table; outputs are staged there too and
-//     flushed as coalesced 128-byte rows.
-// No tensor cores: no step is a dense contraction.  HBM traffic: controls in, audio out.
+// Layout of the computation (DESIGN.md has the derivations; reference citations are to
+// /root/reference/src/model/cpp/*.cpp):
 //
-// Reference citations are to /root/reference/src/model/cpp/*.cpp (see DESIGN.md for the derivation).
+//   * Every string is owned by L lanes of one warp for the whole call.  Transverse block: blocked
+//     layout, ET consecutive grid rows per lane; u^{n-1}, u^{n-2}, the tridiagonal factors and the
+//     right-hand side live in registers; stencil halos move with warp shuffles.
+//   * Only the rows that can differ from zero are solved: R = min(W_t, N_t+3) transverse rows.  The
+//     reference solves all W_t = batch-max rows (misc.cpp:119-127); rows >= N_t+3 form a homogeneous
+//     constant-coefficient tail whose exact effect is a continued-fraction correction of the pivot of
+//     row R-1 (computed once per step).  Strings are therefore sized by their OWN grid, and a launch is
+//     bucketed by (L, ET) so that small strings use few lanes.
+//   * The implicit system  [A11 K_tl; K_lt A22] w = -RHS  (string.cpp:162-181,238) is solved matrix-free:
+//     block Gauss-Seidel over the transverse/longitudinal blocks; A11 (tridiagonal, depends on
+//     Lambda(u^{n-1})) by a register-resident partitioned Thomas factorisation (local LU of the ET-1
+//     interior rows per lane + parallel cyclic reduction over the L interface rows via shuffles);
+//     A22 (constant coefficients, off/diag ~ 1e-5) by Jacobi sweeps folded into the same iteration.
+//     The sweeps stop on the predicted error (measured contraction rate), not on the last change.
+//   * Longitudinal block: shared memory; the linear interpolation operators Int_tl / Int_lt
+//     (misc.cpp:78-105) are gathers whose indices/weights are cached and rebuilt only when a grid
+//     size changes (a few times per second of audio).
+//   * Per-step scalars (grid sizes, loss, operator coefficients; string.cpp:16-41,96-120) are computed
+//     TB steps at a time, one step per lane, into a shared-memory table; outputs are staged there too
+//     and flushed as coalesced rows.
+//   * Groups (reference batches) couple their strings only through the batch-max operator widths and
+//     the any-over-batch convergence votes (string.cpp:252-253, hammer.cpp:51).  The widths come from a
+//     prepass table.  A group without bowed/hammered strings needs no votes (the second fixed-point
+//     pass of an unforced string reproduces the first), so its strings run fully independently
+//     ("independent mode", any warp, no CTA barrier); a group with forced strings runs as one CTA with
+//     __syncthreads_or votes ("grouped mode").
+// No tensor cores: no step is a dense contraction.  HBM traffic: controls in, audio out.
 
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -28,6 +40,7 @@
 #include <map>
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 
 #include "sfdtd.h"
 
@@ -40,19 +53,34 @@
 namespace {
 
 constexpr int WL_MARGIN = 2;        // ghost rows of the longitudinal block kept beyond N_l (decay (e/d)^m, e/d ~ 1e-5)
-constexpr int NV = 20;              // doubles per time step in the per-string scalar table
+constexpr int NV = 28;              // doubles per time step in the per-string scalar table
+constexpr int NI = 8;               // ints per time step
 constexpr int NOUT = 5;             // staged outputs per step
+constexpr int NCONST = 8;           // per-string constants kept in shared memory
 constexpr int GS_CAP = 200;         // cap on block Gauss-Seidel sweeps per solve
-constexpr double GS_TOL = 1e-13;    // relative max-norm change that ends the sweeps
+constexpr float GS_TOL = 1e-13f;    // predicted relative max-norm error that ends the sweeps
+constexpr int NLA_I = 6;            // longitudinal arrays per string, independent mode: Z1 Z2 ZA ZB RL P
+constexpr int NLA_G = 7;            // grouped mode: + ZP (previous fixed-point iterate)
+constexpr int TBS = 8;              // time steps per scalar-table block
 
-// table slots
-enum { T_NT = 0, T_NL, T_HT, T_HL, T_S0K, T_S1K, T_G, T_PHI, T_KK, T_TOLT, T_TOLL, T_XB, T_VB, T_FB, T_WID, T_UHPRE, T_SIG0, T_SIG1 };
+// table slots (doubles)
+enum { T_IHT = 0, T_OFFA, T_DIAGA, T_CORR, T_OFFC, T_DIAGC, T_DIAGB, T_OFF1B, T_KH4, T_PH2, T_PHL, T_IDA, T_EIDA,
+       T_RDW, T_TOLT, T_TOLL, T_CTR, T_VB, T_FB, T_WID, T_UHPRE, T_HT, T_IHL, T_S0K, T_S1K, T_G, T_GA2, T_PHI };
+static_assert(T_PHI < NV, "table too small");
+// table slots (ints)
+enum { I_NT = 0, I_NL, I_R, I_WLS, I_RK, I_KEEPL, I_IDXH, I_IC };
+// per-string constants
+enum { C_WPOW = 0, C_MR, C_AHM1, C_PHI0, C_PHI1, C_RP };
 
 struct KArgs {
     sfdtd_args a;
-    double k, k2, k4, th, omth, tt1, tt2, lamc, order, mhd;
-    const int32_t *maxNt, *maxNl;   // per string, over this call (prepass)
-    const int32_t *group_ids;       // groups handled by this launch
+    double k, ik, k2, k4, th, omth, tt1, tt2, lamc, order, mhd;
+    const int32_t *Wtab;            // [n_groups][Nt]  W_t | W_l << 16  (batch-max operator widths, misc.cpp:119-127)
+    const int32_t *ids;             // independent mode: string ids; grouped mode: group ids
+    int32_t n_items;                // entries of ids
+    const int32_t *maxNl;           // per string: largest N_l of this call (prepass); sizes the longitudinal block in grouped mode
+    int32_t WLp;                    // independent mode: longitudinal rows allocated per string (incl. guards)
+    int32_t need_xax;               // copy the bow axis to shared memory
     int32_t max_iter;
 };
 
@@ -63,7 +91,19 @@ __device__ __forceinline__ double lds(const sfdtd_array &A, int b) {
     return ((const double *)A.ptr)[(int64_t)b * A.bs];
 }
 
+// 1/x to full double precision without the slow-path branch of the IEEE division (MUFU.RCP64H + 2 Newton steps)
+__device__ __forceinline__ double frcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 // ---- get_derived_vars (string.cpp:16-41), reference operation order, no FMA contraction ----------
+// floor(1/h) decides the grid sizes: one ulp flips them, so this part is evaluated exactly like the reference.
 struct Derived { double gamma, K, Nt, ht, Nl, hl; };
 __device__ __forceinline__ Derived derive(double f0, double kappa_rel, double alpha, const KArgs &A) {
     Derived d;
@@ -86,8 +126,9 @@ __device__ __forceinline__ Derived derive(double f0, double kappa_rel, double al
     d.gamma = gamma; d.K = K;
     return d;
 }
+__device__ __forceinline__ int clampN(double v) { return (int)fmin(fmax(v, 0.0), 60000.0); }   // NaN -> 0
 
-// ---- prepass: per string, the largest N_t / N_l any step of this call can see (at min f0) ----------
+// ---- prepass 1: per string, the largest N_t / N_l any step of this call can see (at min f0) ----------
 __global__ void sfdtd_prepass_kernel(const __grid_constant__ KArgs A, int32_t *maxNt, int32_t *maxNl) {
     const int b = blockIdx.x;
     const int Nt = A.a.Nt;
@@ -104,11 +145,25 @@ __global__ void sfdtd_prepass_kernel(const __grid_constant__ KArgs A, int32_t *m
     if (threadIdx.x == 0) {
         for (int w = 1; w < (blockDim.x >> 5); w++) fm = fm < sm[w] ? fm : sm[w];
         Derived d = derive(fm, lds(A.a.kappa, b), lds(A.a.alpha, b), A);
-        double nt = d.Nt, nl = d.Nl;
-        if (!(nt >= 0)) nt = 0; if (!(nl >= 0)) nl = 0;
-        if (nt > 1e6) nt = 1e6; if (nl > 1e6) nl = 1e6;
-        maxNt[b] = (int32_t)nt; maxNl[b] = (int32_t)nl;
+        maxNt[b] = clampN(d.Nt); maxNl[b] = clampN(d.Nl);
     }
+}
+
+// ---- prepass 2: batch-max operator widths per (group, step) (misc.cpp:119-127) ------------------------
+__global__ void sfdtd_width_kernel(const __grid_constant__ KArgs A, int32_t *Wtab) {
+    const int g = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Nt = A.a.Nt;
+    if (n >= Nt) return;
+    const int g0 = g * A.a.group_size;
+    const int G = min(A.a.group_size, A.a.B - g0);
+    int wt = 0, wl = 0;
+    for (int s = 0; s < G; s++) {
+        const int b = g0 + s;
+        const Derived d = derive(ldx(A.a.f0, b, n), lds(A.a.kappa, b), lds(A.a.alpha, b), A);
+        wt = max(wt, clampN(d.Nt)); wl = max(wl, clampN(d.Nl));
+    }
+    Wtab[(int64_t)g * Nt + n] = (wt + 1) | ((wl + 1) << 16);
 }
 
 // ---- warp helpers over the L lanes of one string -------------------------------------------------
@@ -132,6 +187,12 @@ template <int L> __device__ __forceinline__ int red_or(int v) {
 }
 template <int L> constexpr int ilog2() { return L <= 1 ? 0 : 1 + ilog2<L / 2>(); }
 
+// fmaxf drops NaN operands: a NaN anywhere must still end the sweeps, so NaN is mapped to +inf here
+__device__ __forceinline__ float absf_nan_inf(double v) {
+    const float f = fabsf((float)v);
+    return (f != f) ? INFINITY : f;
+}
+
 __device__ __forceinline__ double nan0(double v) {   // nan_to_num (string.cpp:225-226)
     if (v != v) return 0.0;
     if (isinf(v)) return v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
@@ -149,8 +210,8 @@ template <int L, int ET> struct TriSolver {
         double cprev = 0.0;
 #pragma unroll
         for (int r = 0; r < M; r++) {
-            const double den = b[r] - a[r] * cprev;
-            inv[r] = __drcp_rn(den);
+            const double den = fma(-a[r], cprev, b[r]);
+            inv[r] = frcp(den);
             cp[r] = c[r] * inv[r];
             lw[r] = a[r] * inv[r];
             cprev = cp[r];
@@ -161,7 +222,7 @@ template <int L, int ET> struct TriSolver {
         for (int r = 1; r < M; r++) V[r] = -lw[r] * V[r - 1];
         W[M - 1] = cp[M - 1];
 #pragma unroll
-        for (int r = M - 2; r >= 0; r--) { V[r] = V[r] - cp[r] * V[r + 1]; W[r] = -cp[r] * W[r + 1]; }
+        for (int r = M - 2; r >= 0; r--) { V[r] = fma(-cp[r], V[r + 1], V[r]); W[r] = -cp[r] * W[r + 1]; }
         ae = a[ET - 1]; ce = c[ET - 1];
         const double Vn0 = shdn<L>(V[0], 1), Wn0 = shdn<L>(W[0], 1);
         double Ar = -ae * V[M - 1];
@@ -172,7 +233,7 @@ template <int L, int ET> struct TriSolver {
 #pragma unroll
         for (int lv = 0; lv < LV; lv++) {
             const int s = 1 << lv;
-            const double iB = __drcp_rn(Br);
+            const double iB = frcp(Br);
             const double iBm = shup<L>(iB, s), iBp = shdn<L>(iB, s);
             const double Am = shup<L>(Ar, s), Cm = shup<L>(Cr, s);
             const double Ap = shdn<L>(Ar, s), Cp = shdn<L>(Cr, s);
@@ -183,7 +244,7 @@ template <int L, int ET> struct TriSolver {
             Ar = hm ? -Am * q1 : 0.0;
             Cr = hp ? -Cp * q2 : 0.0;
         }
-        invB = __drcp_rn(Br);
+        invB = frcp(Br);
     }
 
     // d: right-hand side in, solution out
@@ -191,9 +252,9 @@ template <int L, int ET> struct TriSolver {
         double Y[M];
         Y[0] = d[0] * inv[0];
 #pragma unroll
-        for (int r = 1; r < M; r++) Y[r] = d[r] * inv[r] - lw[r] * Y[r - 1];
+        for (int r = 1; r < M; r++) Y[r] = fma(-lw[r], Y[r - 1], d[r] * inv[r]);
 #pragma unroll
-        for (int r = M - 2; r >= 0; r--) Y[r] = Y[r] - cp[r] * Y[r + 1];
+        for (int r = M - 2; r >= 0; r--) Y[r] = fma(-cp[r], Y[r + 1], Y[r]);
         double Yn0 = shdn<L>(Y[0], 1);
         if (ln == L - 1) Yn0 = 0.0;
         double D = d[ET - 1] - ae * Y[M - 1] - ce * Yn0;
@@ -213,14 +274,13 @@ template <int L, int ET> struct TriSolver {
 };
 
 // float32 linear-interpolation row (misc.cpp:78-105; F.interpolate(..., 'linear', align_corners=True) on float32)
-__device__ __forceinline__ void interp_row(float s, int o, int in_last, int &i0, int &i1, double &w0, double &w1) {
+__device__ __forceinline__ void interp_row(float s, int o, int in_last, int &i0, int &i1, float &w0, float &w1) {
     const float r = __fmul_rn(s, (float)o);
     int a0 = (int)r;
     a0 = a0 > in_last ? in_last : a0;
     i0 = a0; i1 = a0 + (a0 < in_last ? 1 : 0);
-    const float l1 = __fsub_rn(r, (float)a0);
-    const float l0 = __fsub_rn(1.0f, l1);
-    w0 = (double)l0; w1 = (double)l1;
+    w1 = __fsub_rn(r, (float)a0);
+    w0 = __fsub_rn(1.0f, w1);
 }
 
 // select element `slot` of a register array without dynamic indexing
@@ -236,100 +296,162 @@ template <int L, int ET> __device__ __forceinline__ double fetch_row(const doubl
     return shix<L>(mine, idx / ET);
 }
 
+
+
+// shared-memory doubles of the fixed part of a string slot, and of its longitudinal part (W rows incl. guards, W even)
+__host__ __device__ inline int slot_fixed_doubles(int L, int ET, bool grouped) {
+    const int LE = L * ET;
+    int n = TBS * NV + TBS * NI / 2 + TBS * NOUT + NCONST + (LE + 2) + 2 * (LE + 4) + (grouped ? LE : 0);
+    n = (n + 1) & ~1;                 // 16-byte aligned slots (int4 / double2 loads)
+    if ((n & 15) == 0) n += 2;        // ... that do not start in the same bank
+    return n;
+}
+__host__ __device__ inline int slot_long_doubles(int W, bool grouped) { return ((grouped ? NLA_G : NLA_I) * W + 2 * W + (W + 1) / 2 + 1) & ~1; }
+__host__ __device__ inline int long_rows(int maxNl) { return (maxNl + 1 + WL_MARGIN + 2 + 1) & ~1; }   // + 2 guards, even
+
 // ======================================================================================================
-template <int L, int ET, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) sfdtd_step_kernel(const __grid_constant__ KArgs A) {
-    constexpr int TB = L;   // time steps per scalar-table block
-    extern __shared__ double smem[];
+template <int L, int ET, bool GROUPED, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_constant__ KArgs A) {
+    constexpr int TB = TBS;
+    constexpr int LE = L * ET;
+    constexpr int NLA = GROUPED ? NLA_G : NLA_I;
+    // fixed slot layout (offsets in doubles)
+    constexpr int O_TABI = TB * NV, O_OST = O_TABI + TB * NI / 2, O_CST = O_OST + TB * NOUT, O_QS = O_CST + NCONST;
+    constexpr int O_UA = O_QS + LE + 2 + 2, O_UB = O_UA + LE + 4, O_RC = O_UB + LE + 2;
+    extern __shared__ __align__(16) double smem[];
     const sfdtd_args &a = A.a;
     const int tid = threadIdx.x;
     const int sl = tid / L, ln = tid % L;
     const int nslots = blockDim.x / L;
-    const int gid = A.group_ids[blockIdx.x];
-    const int g0 = gid * a.group_size;
-    const int G = min(a.group_size, a.B - g0);
-    const bool valid = sl < G;
-    const int b = g0 + (valid ? sl : G - 1);     // spare slots shadow the last string and never write or vote
+    int b; bool valid;
+    if (GROUPED) {
+        const int gid = A.ids[blockIdx.x];
+        const int g0 = gid * a.group_size;
+        const int G = min(a.group_size, a.B - g0);
+        valid = sl < G;
+        b = g0 + (valid ? sl : G - 1);           // spare slots shadow the last string and never write or vote
+    } else {
+        const int item = blockIdx.x * nslots + sl;
+        valid = item < A.n_items;
+        b = A.ids[valid ? item : A.n_items - 1];
+    }
     const int Nt = a.Nt, NXT = a.Nx_t1, NXL = a.Nx_l1;
     const bool surf = a.flags & SFDTD_SURFACE_INTEGRAL;
     const bool save_state = a.flags & SFDTD_SAVE_STATE;
     const bool skip_aux = a.flags & SFDTD_SKIP_AUX;
-    const double kk = A.k, k2 = A.k2;
     uint32_t status = 0;
 
-    // ---- shared memory carve-up ----
-    const int WLa = A.maxNl[b] + 1 + WL_MARGIN;              // rows allocated for this string's longitudinal block
-    int *ioffs = (int *)smem;                                // [nslots+1] l-block offsets (doubles)
-    int *gN = ioffs + (nslots + 2);                          // [2][TB][nslots]
-    int *gW = gN + 2 * TB * nslots;                          // [2][TB]
-    float *xaxs = (float *)(gW + 2 * TB);                    // [NXT]
-    size_t cur_off = ((size_t)((char *)(xaxs + NXT) - (char *)smem) + 7) / 8;
-    double *tab_all = smem + cur_off; cur_off += (size_t)nslots * TB * NV;
-    double *ost_all = smem + cur_off; cur_off += (size_t)nslots * TB * (NOUT + 1);
-    double *qs_all = smem + cur_off;  cur_off += (size_t)nslots * (L * ET + 2);
-    double *lblk_all = smem + cur_off;
-    if (ln == 0) ioffs[sl + 1] = 6 * (WLa + 2);
-    for (int i = tid; i < NXT; i += blockDim.x) xaxs[i] = a.xax[i];
-    __syncthreads();
-    if (tid == 0) { ioffs[0] = 0; for (int s = 0; s < nslots; s++) ioffs[s + 1] += ioffs[s]; }
-    __syncthreads();
-    double *tab = tab_all + (size_t)sl * TB * NV;
-    double *ost = ost_all + (size_t)sl * TB * (NOUT + 1);
-    double *qs = qs_all + (size_t)sl * (L * ET + 2);
-    double *lb = lblk_all + ioffs[sl];
-    const int WLp = WLa + 2;
-    double *Z1 = lb, *Z2 = lb + WLp, *ZP = lb + 2 * WLp, *ZA = lb + 3 * WLp, *ZB = lb + 4 * WLp, *RL = lb + 5 * WLp;
+    // ---- shared memory carve-up: [bow axis][fixed slot parts][longitudinal parts] ----
+    float *xaxs = (float *)smem;                                      // [NXT] (only when the bow axis is needed)
+    const int xoff = A.need_xax ? (((NXT + 3) / 4) * 2) : 0;
+    double *const S = smem + xoff + (size_t)sl * slot_fixed_doubles(L, ET, GROUPED);
+    double *Lb = smem + xoff + (size_t)nslots * slot_fixed_doubles(L, ET, GROUPED);
+    int WLp;
+    if (GROUPED) {
+        // per-string longitudinal allocation (sized by the string's own largest N_l), offsets by a prefix sum
+        int *ioffs = (int *)Lb;                                       // [nslots + 2]
+        WLp = long_rows(A.maxNl[b]);
+        if (ln == 0) ioffs[sl + 1] = slot_long_doubles(WLp, true);
+        __syncthreads();
+        if (tid == 0) { ioffs[0] = ((nslots + 2) / 2 + 1) & ~1; for (int q = 0; q < nslots; q++) ioffs[q + 1] += ioffs[q]; }
+        __syncthreads();
+        const int off = ioffs[sl];
+        __syncthreads();
+        Lb += off;
+    } else {
+        WLp = A.WLp;
+        Lb += (size_t)sl * slot_long_doubles(WLp, false);
+    }
+    const int WLa = WLp - 2;                                          // usable longitudinal rows (guards at -1 and WLa)
+    double *const tab = S;                                            // [TB][NV]
+    int *const tabi = (int *)(S + O_TABI);                            // [TB][NI]
+    double *const ost = S + O_OST;                                    // [TB][NOUT]
+    double *const cst = S + O_CST;                                    // [NCONST]
+    double *const qs = S + O_QS;                                      // [LE + 2]
+    double *const RC = S + O_RC;                                      // [LE] bow weights (grouped mode only)
+    double *const LW = Lb + NLA * WLp;                                // [WLp][2] Int_lt weights
+    int *const LI = (int *)(LW + 2 * WLp);                            // [WLp]    Int_lt indices i0 | i1 << 16
+    // transverse state rows n-1 / n-2 (in S, guards: 2 each side) and longitudinal arrays (in Lb, guard at [-1]); offsets swap
+    int u1o = O_UA, u2o = O_UB;
+    int z1o = 1, z2o = WLp + 1;
+    const int zao = 2 * WLp + 1, zbo = 3 * WLp + 1, rlo = 4 * WLp + 1, po = 5 * WLp + 1, zpo = 6 * WLp + 1;
+    if (A.need_xax) {
+        for (int i = tid; i < NXT; i += blockDim.x) xaxs[i] = a.xax[i];
+        __syncthreads();
+    }
 
     // ---- per-string constants ----
-    const double kappa_rel = lds(a.kappa, b), alpha = lds(a.alpha, b), rp = lds(a.pos, b);
-    const double *T60 = (const double *)a.T60.ptr + (int64_t)b * a.T60.bs;
-    const double T00 = T60[0], T01 = T60[1], T10 = T60[2], T11 = T60[3];
-    const double phi0 = lds(a.phi_0, b), phi1 = lds(a.phi_1, b);
-    const double xH = lds(a.x_H, b), aH = lds(a.alpha_H, b);
-    const double wH = lds(a.w_H, b) / A.lamc, Mr = lds(a.M_r, b) / A.lamc;
-    const double wpow = pow(wH, 1.0 + aH);
     const bool bowm = a.bow_mask[b] != 0, hamm = a.hammer_mask[b] != 0;
-    const double bm = bowm ? 1.0 : 0.0, hm = hamm ? 1.0 : 0.0;
     const bool forced = bowm || hamm;
-    const int group_has_hammer = __syncthreads_or(valid && hamm);
-    const int group_has_bow = __syncthreads_or(valid && bowm);
+    bool group_has_hammer = false, group_has_bow = false;
+    if (GROUPED) {
+        group_has_hammer = __syncthreads_or(valid && hamm);
+        group_has_bow = __syncthreads_or(valid && bowm);
+    }
     // CTA-uniform compute switches (they guard shuffles and barriers); per-string output switches
     const bool do_bow = group_has_bow || !skip_aux, do_ham = group_has_hammer || !skip_aux;
     const bool out_bow = bowm || !skip_aux, out_ham = hamm || !skip_aux;
-    const double alpha2 = alpha * alpha;
+    if (ln == 0) {
+        const double aH = lds(a.alpha_H, b);
+        const double wH = lds(a.w_H, b) / A.lamc;
+        cst[C_WPOW] = pow(wH, 1.0 + aH);
+        cst[C_MR] = lds(a.M_r, b) / A.lamc;
+        cst[C_AHM1] = aH - 1.0;
+        cst[C_PHI0] = lds(a.phi_0, b); cst[C_PHI1] = lds(a.phi_1, b);
+        cst[C_RP] = lds(a.pos, b);
+    }
 
     // ---- initial state: rows n-2, n-1 ----
-    double u1[ET], u2[ET];
     {
+        for (int j = ln; j < 2 * LE + 10 + (GROUPED ? LE : 0); j += L) S[O_QS + LE + j] = 0.0;      // UA, UB (with guards), RC
+        for (int j = ln; j < NLA * WLp; j += L) Lb[j] = 0.0;
+        for (int j = ln; j < WLp; j += L) { LW[2 * j] = 0.0; LW[2 * j + 1] = 0.0; LI[j] = 0; }
+        __syncwarp();
         const double *su = (const double *)a.state_u.ptr + (int64_t)b * a.state_u.bs;
 #pragma unroll
         for (int r = 0; r < ET; r++) {
             const int i = ln * ET + r;
-            u2[r] = (i < NXT) ? su[i] : 0.0;
-            u1[r] = (i < NXT) ? su[a.state_u.ts + i] : 0.0;
+            S[u2o + i] = (i < NXT) ? su[i] : 0.0;
+            S[u1o + i] = (i < NXT) ? su[a.state_u.ts + i] : 0.0;
         }
         const double *sz = (const double *)a.state_z.ptr + (int64_t)b * a.state_z.bs;
-        for (int j = ln; j < WLp; j += L) {
-            Z2[j] = (j < NXL && j < WLa) ? sz[j] : 0.0;
-            Z1[j] = (j < NXL && j < WLa) ? sz[a.state_z.ts + j] : 0.0;
-            ZP[j] = 0.0; ZA[j] = 0.0; ZB[j] = 0.0; RL[j] = 0.0;
+        for (int j = ln; j < WLa; j += L) {
+            Lb[z2o + j] = (j < NXL) ? sz[j] : 0.0;
+            Lb[z1o + j] = (j < NXL) ? sz[a.state_z.ts + j] : 0.0;
         }
     }
     double uH1 = 0.0, uH2 = 0.0;
     if (Nt > 2) { uH2 = ldx(a.u_H, b, 0); uH1 = ldx(a.u_H, b, 1); }
-    double sig0_last = 0.0, sig1_last = 0.0;
-    int64_t cnt_outer = 0, cnt_sweeps = 0, cnt_ham = 0, cnt_steps = 0;
+    uint32_t cnt_outer = 0, cnt_sweeps = 0, cnt_ham = 0, cnt_steps = 0;
+    // cached interpolation rows of Int_tl for this lane's transverse rows (rebuilt when a grid size changes):
+    // indices are stored +1 so that 0 addresses the zero guard (rows beyond N_t)
+    int tix[ET]; float twb[ET];
+#pragma unroll
+    for (int r = 0; r < ET; r++) { tix[r] = 0; twb[r] = 0.f; }
+    int curNt = -1, curNl = -1, ext1 = WLa, ext2 = WLa;               // ext: rows of Z1 / Z2 that may be non-zero
+    float rho_h = 0.5f;                                               // contraction-rate history of the block iteration
     __syncwarp();
 
     for (int n0 = 2; n0 < Nt; n0 += TB) {
         // ================= scalar table for steps n0 .. n0+TB-1 (one step per lane) =================
         {
-            const int n = n0 + ln;
-            double *t = tab + ln * NV;
-            int iNt = 0, iNl = 0;
-            if (n < Nt) {
+            const double kappa_rel = lds(a.kappa, b), alpha = lds(a.alpha, b);
+            const double *T60 = (const double *)a.T60.ptr + (int64_t)b * a.T60.bs;
+            const double T00 = T60[0], T01 = T60[1], T10 = T60[2], T11 = T60[3];
+            const double alpha2 = alpha * alpha;
+            const double xH = lds(a.x_H, b);
+            const double exc = 1.0 + (hamm ? 1.0 : 0.0) + (bowm ? 1.0 : 0.0);
+            const int32_t *Wrow = A.Wtab + (int64_t)(b / a.group_size) * Nt;
+            for (int s = ln; s < TB; s += L) {
+                const int n = n0 + s;
+                if (n >= Nt) break;
+                double *t = tab + s * NV;
+                int *ti = tabi + s * NI;
                 const double f0 = ldx(a.f0, b, n);
                 const Derived d = derive(f0, kappa_rel, alpha, A);
+                const int N_t = clampN(d.Nt), N_l = clampN(d.Nl);
+                const int32_t w = Wrow[n];
+                const int Wt = w & 0xffff, Wl = (w >> 16) & 0xffff;
                 // loss parameters (string.cpp:100-120)
                 const double g2 = d.gamma * d.gamma, g4 = g2 * g2;
                 double z1, z2;
@@ -342,437 +464,579 @@ __global__ void __launch_bounds__(MAXT, 1) sfdtd_step_kernel(const __grid_consta
                 const double s0 = m ? (-z2 / T01 + z1 / T11) : 0.0, s1 = m ? (1 / T01 - 1 / T11) : 0.0;
                 const double c6 = 13.815510557964274;   // 6*log(10)
                 const double sig0 = (c6 * s0) / (z1 - z2), sig1 = (c6 * s1) / (z1 - z2);
-                const double g = g2 * k2;
-                t[T_NT] = d.Nt; t[T_NL] = d.Nl; t[T_HT] = d.ht; t[T_HL] = d.hl;
-                t[T_S0K] = (2 * sig0) * kk; t[T_S1K] = (2 * sig1) * kk;
-                t[T_G] = g; t[T_PHI] = (g * (alpha2 - 1)) / 4; t[T_KK] = (d.K * d.K) * k2;
+                const double g = g2 * A.k2;
+                const double s0k = (2 * sig0) * A.k, s1k = (2 * sig1) * A.k;
+                const double phi = (g * (alpha2 - 1)) / 4;
+                const double Kk = (d.K * d.K) * A.k2;
+                const double iht = d.Nt, ihl = d.Nl;          // 1/h_t = N_t exactly
+                const double iht2 = iht * iht, iht4 = iht2 * iht2, ihl2 = ihl * ihl;
+                // operator coefficients (string.cpp:138-181; misc.cpp:119-166)
+                const double diagA = A.th + s0k + 2 * s1k * iht2, offA = 0.5 * A.omth - s1k * iht2;
+                const double kh4 = Kk * iht4;
+                const double dA = (1 + s0k) + 2 * s1k * ihl2, eA = -s1k * ihl2, idA = 1.0 / dA;
+                // bow window on the Nx_t1-point axis (bow.cpp:32, misc.cpp:20-34)
+                const double Nd = (double)NXT;
+                const double xb = ldx(a.x_b, b, n), wd = ldx(a.wid, b, n);
+                const double ctr = __ddiv_rn(__dmul_rn(xb, (double)(N_t - 1)), Nd);
+                const double wid = __ddiv_rn(__dmul_rn(__dmul_rn(wd, d.ht), (double)(N_t - 1)), Nd);
+                const int ic = (int)fmin(fmax(floor((ctr - wid * 0.5) * Nd) - 2, 0.0), 60000.0);
+                // rows that are solved: R (see header); forced rows of a bowed string extend it
+                int R = N_t + 3;
+                if (bowm) { const int Rb = (int)fmin(fmax(ceil((ctr + wid * 0.5) * Nd) + 1, 0.0), 60000.0); R = max(R, Rb); }
+                R = min(R, Wt);
+                int oob = 0;
+                if (R > LE) { R = LE; oob = 1; }
+                // homogeneous tail R..W_t-1 of A11 folded into the pivot of row R-1
+                double corr = 0.0;
+                {
+                    const int mt = Wt - R;
+                    if (mt > 0 && !oob) {
+                        const double o2 = offA * offA;
+                        double pv = diagA;
+                        for (int j = 1; j < mt; j++) { const double pn = diagA - o2 * frcp(pv); if (pn == pv) break; pv = pn; }
+                        corr = o2 * frcp(pv);
+                    }
+                }
+                int WLs = min(N_l + 1 + WL_MARGIN, Wl);
+                if (WLs > WLa) { WLs = WLa; oob = 1; }
+                const int keep_flat = N_t + N_l + 2;                         // string.cpp:233
+                t[T_IHT] = iht; t[T_IHL] = ihl; t[T_HT] = d.ht;
+                t[T_OFFA] = offA; t[T_DIAGA] = diagA; t[T_CORR] = corr;
+                t[T_OFFC] = 0.5 * A.omth + s1k * iht2; t[T_DIAGC] = A.th - s0k - 2 * s1k * iht2;
+                t[T_DIAGB] = -2 * A.th + 2 * g * iht2 + 6 * kh4; t[T_OFF1B] = -A.omth - g * iht2 - 4 * kh4; t[T_KH4] = kh4;
+                t[T_PH2] = phi * iht2; t[T_PHL] = (phi != 0.0) ? ihl * d.ht : 0.0; t[T_PHI] = phi;
+                t[T_IDA] = idA; t[T_EIDA] = eA * idA;
+                t[T_RDW] = ((0.5 * d.ht) * exc) * A.ik;                      // surface-integral weight / k (string.cpp:274-291)
                 t[T_TOLT] = pow(d.ht, A.order); t[T_TOLL] = pow(d.hl, A.order);
-                t[T_XB] = ldx(a.x_b, b, n); t[T_VB] = ldx(a.v_b, b, n); t[T_FB] = ldx(a.F_b, b, n); t[T_WID] = ldx(a.wid, b, n);
+                t[T_CTR] = ctr; t[T_WID] = wid;
+                t[T_VB] = ldx(a.v_b, b, n); t[T_FB] = ldx(a.F_b, b, n);
                 t[T_UHPRE] = ldx(a.u_H, b, n);
-                t[T_SIG0] = sig0; t[T_SIG1] = sig1;
-                iNt = (int)fmin(fmax(d.Nt, 0.0), 1e6); iNl = (int)fmin(fmax(d.Nl, 0.0), 1e6);
+                t[T_S0K] = s0k; t[T_S1K] = s1k; t[T_G] = g; t[T_GA2] = g * alpha2;
+                ti[I_NT] = N_t; ti[I_NL] = N_l; ti[I_R] = R | (oob << 30); ti[I_WLS] = WLs;
+                ti[I_RK] = min(R, keep_flat); ti[I_KEEPL] = keep_flat - NXT;
+                ti[I_IDXH] = (int)fmin(fmax(floor(__dmul_rn(xH, (double)(N_t - 1))), 0.0), (double)(LE - 1));
+                ti[I_IC] = ic;
             }
-            gN[(0 * TB + ln) * nslots + sl] = valid ? iNt : 0;
-            gN[(1 * TB + ln) * nslots + sl] = valid ? iNl : 0;
         }
-        __syncthreads();
-        for (int q = tid; q < 2 * TB; q += blockDim.x) {
-            int mx = 0;
-            for (int s = 0; s < nslots; s++) mx = max(mx, gN[q * nslots + s]);
-            gW[q] = mx + 1;                         // W_t / W_l = batch-max width (misc.cpp:119-127)
-        }
-        __syncthreads();
+        __syncwarp();
 
         const int jmax = min(TB, Nt - n0);
         for (int jj = 0; jj < jmax; jj++) {
             const int n = n0 + jj;
             const double *t = tab + jj * NV;
-            int Wt = gW[jj], Wl = gW[TB + jj];
-            const int N_t = (int)t[T_NT], N_l = (int)t[T_NL];
-            const double ht = t[T_HT], iht = t[T_NT], ihl = t[T_NL];
-            const double s0k = t[T_S0K], s1k = t[T_S1K], g = t[T_G], phi = t[T_PHI], Kk = t[T_KK];
-            const double tol_t = t[T_TOLT], tol_l = t[T_TOLL];
-            if (Wt > L * ET) { Wt = L * ET; status |= SFDTD_ST_RANGE; }
-            int WLs = min(N_l + 1 + WL_MARGIN, Wl);
-            if (WLs > WLa) { WLs = WLa; status |= SFDTD_ST_RANGE; }
-            const int keep_flat = N_t + N_l + 2;            // string.cpp:233
-            const int keep_l = keep_flat - NXT;             // l rows j < keep_l keep their base RHS
-            const double iht2 = iht * iht, iht4 = iht2 * iht2, ihl2 = ihl * ihl;
-            const double diagA = A.th + s0k + 2 * s1k * iht2, offA = 0.5 * A.omth - s1k * iht2;
-            const double diagC = A.th - s0k - 2 * s1k * iht2, offC = 0.5 * A.omth + s1k * iht2;
-            const double kh4 = Kk * iht4;
-            const double diagB = -2 * A.th + 2 * g * iht2 + 6 * kh4, off1B = -A.omth - g * iht2 - 4 * kh4, off2B = kh4;
-            const double ph2 = phi * iht2;
-            const double dA = (1 + s0k) + 2 * s1k * ihl2, eA = -s1k * ihl2, idA = 1.0 / dA;
-            const bool coupled = (phi != 0.0);
-            const float s_tl = (N_t > 0) ? __fdiv_rn((float)N_l, (float)N_t) : 0.0f;    // t-row -> l-grid
-            const float s_lt = (N_l > 0) ? __fdiv_rn((float)N_t, (float)N_l) : 0.0f;    // l-row -> t-grid
+            const int4 tiA = *(const int4 *)(tabi + jj * NI);
+            const int N_t = tiA.x, N_l = tiA.y, R = tiA.z & 0xffffff, WLs = tiA.w;
+            if (tiA.z >> 30) status |= SFDTD_ST_RANGE;
 
-            // ---- masked previous states (mask_1d, string.cpp:129-132) and halos ----
-            double m1[ET], m2[ET];
-#pragma unroll
-            for (int r = 0; r < ET; r++) {
-                const int i = ln * ET + r;
-                m1[r] = (i <= N_t) ? u1[r] : u1[r] * 0.0;
-                m2[r] = (i <= N_t) ? u2[r] : u2[r] * 0.0;
-            }
-            double e1[ET + 4];
-            {
-                double l2 = shup<L>(m1[ET - 2], 1), l1 = shup<L>(m1[ET - 1], 1);
-                double r0 = shdn<L>(m1[0], 1), r1 = shdn<L>(m1[1], 1);
-                if (ln == 0) { l2 = 0.0; l1 = 0.0; }
-                if (ln == L - 1) { r0 = 0.0; r1 = 0.0; }
-                e1[0] = l2; e1[1] = l1; e1[ET + 2] = r0; e1[ET + 3] = r1;
-#pragma unroll
-                for (int r = 0; r < ET; r++) e1[r + 2] = m1[r];
-            }
-            double m2l = shup<L>(m2[ET - 1], 1), m2r = shdn<L>(m2[0], 1);
-            if (ln == 0) m2l = 0.0;
-            if (ln == L - 1) m2r = 0.0;
-            // Lambda = Dxb u1 (string.cpp:152), rows < W_t
-            double lam[ET + 1];
-#pragma unroll
-            for (int r = 0; r < ET; r++) {
-                const int i = ln * ET + r;
-                lam[r] = (i < Wt) ? (e1[r + 2] - e1[r + 1]) * iht : 0.0;
-            }
-            lam[ET] = shdn<L>(lam[0], 1);
-            if (ln == L - 1) lam[ET] = 0.0;
-
-            // t-row interpolation parameters onto the l grid (Int_tl)
-            int ti0[ET], ti1[ET]; float tw0[ET], tw1[ET];
-#pragma unroll
-            for (int r = 0; r < ET; r++) {
-                const int i = ln * ET + r;
-                double w0, w1;
-                interp_row(s_tl, i, N_l, ti0[r], ti1[r], w0, w1);
-                tw0[r] = (float)w0; tw1[r] = (float)w1;
-                if (i > N_t) { tw0[r] = 0.0f; tw1[r] = 0.0f; ti0[r] = 0; ti1[r] = 0; }
-                ti0[r] = min(ti0[r], WLp - 1); ti1[r] = min(ti1[r], WLp - 1);
-            }
-
-            // ---- A11 (string.cpp:153-162) ----
-            double ca[ET], cb[ET], cc[ET];
-#pragma unroll
-            for (int r = 0; r < ET; r++) {
-                const int i = ln * ET + r;
-                const double l2 = lam[r] * lam[r], lp2 = lam[r + 1] * lam[r + 1];
-                const bool in = i < Wt;
-                ca[r] = (in && i > 0) ? offA - ph2 * l2 : 0.0;
-                cc[r] = (in && i + 1 < Wt) ? offA - ph2 * lp2 : 0.0;
-                cb[r] = in ? diagA + ph2 * (l2 + lp2) : 1.0;
-            }
-            TriSolver<L, ET> ts;
-            ts.factor(ca, cb, cc, ln);
-
-            // ---- base RHS  B w1 + C w2  (string.cpp:223-224) ----
-            double rt[ET];
-            // K_tl (2 z1 + z2): stage zz in ZA
-            for (int j = ln; j < WLp; j += L) ZA[j] = (j <= N_l && j < WLa) ? 2.0 * Z1[j] + Z2[j] : 0.0;
-            __syncwarp();
-            {
-                double y[ET];
-#pragma unroll
-                for (int r = 0; r < ET; r++) y[r] = coupled ? (double)tw0[r] * ZA[ti0[r]] + (double)tw1[r] * ZA[ti1[r]] : 0.0;
-                double yl = shup<L>(y[ET - 1], 1);
-                if (ln == 0) yl = 0.0;
-                double q[ET + 1];
-#pragma unroll
-                for (int r = 0; r < ET; r++) q[r] = lam[r] * ((y[r] - (r == 0 ? yl : y[r - 1])) * iht);
-                q[ET] = shdn<L>(q[0], 1);
-                if (ln == L - 1) q[ET] = 0.0;
+            // ---- interpolation rows, rebuilt only when a grid size changed (misc.cpp:78-105) ----
+            const bool grid_changed = (N_t != curNt) || (N_l != curNl);
+            if (__any_sync(FULLMASK, grid_changed)) {
+              if (grid_changed) {
+                const float s_tl = (N_t > 0) ? __fdiv_rn((float)N_l, (float)N_t) : 0.0f;    // t-row -> l-grid
+                const float s_lt = (N_l > 0) ? __fdiv_rn((float)N_t, (float)N_l) : 0.0f;    // l-row -> t-grid
 #pragma unroll
                 for (int r = 0; r < ET; r++) {
                     const int i = ln * ET + r;
-                    const double l2 = lam[r] * lam[r], lp2 = lam[r + 1] * lam[r + 1];
-                    double d4 = diagB;
-                    if (i == 1 || i == N_t - 1) d4 += kh4;          // Dxxxx_clamped (misc.cpp:146-163)
-                    const double Bu = d4 * e1[r + 2] + off1B * (e1[r + 1] + e1[r + 3]) + off2B * (e1[r] + e1[r + 4]);
-                    const double m2m = (r == 0) ? m2l : m2[r - 1], m2p = (r == ET - 1) ? m2r : m2[r + 1];
-                    const double Cu = (diagC + ph2 * (l2 + lp2)) * m2[r] + (offC - ph2 * l2) * m2m + (offC - ph2 * lp2) * m2p;
-                    const double Kz = -phi * ((q[r + 1] - q[r]) * iht);
-                    rt[r] = (i < Wt && i < keep_flat) ? (Bu + Cu + Kz) : 0.0;
+                    int i0, i1; float w0, w1;
+                    interp_row(s_tl, i, N_l, i0, i1, w0, w1);
+                    i0 = min(i0, WLa - 1) + 1; i1 = min(i1, WLa - 1) + 1;
+                    if (i > N_t) { w1 = 0.f; i0 = 0; i1 = 0; }
+                    tix[r] = i0 | (i1 << 16); twb[r] = w1;
                 }
-            }
-            // l-block base RHS, only when the flat-index mask leaves any of it (string.cpp:233)
-            const bool has_rl = keep_l > 0;
-            if (__any_sync(FULLMASK, has_rl)) {
-                // q2 = Lam Dxb u2 -> smem, then K_lt u2 by gathers
-#pragma unroll
-                for (int r = 0; r < ET; r++) qs[ln * ET + r] = lam[r] * ((m2[r] - (r == 0 ? m2l : m2[r - 1])) * iht);
-                __syncwarp();
-                const double dB = -2 + 2 * (g * alpha2) * ihl2, eB = -(g * alpha2) * ihl2;
-                const double dC = (1 - s0k) - 2 * s1k * ihl2, eC = s1k * ihl2;
-                for (int j = ln; j < WLs; j += L) {
-                    double v = 0.0;
-                    if (has_rl && j < keep_l) {
-                        const double z1c = (j <= N_l) ? Z1[j] : 0.0, z2c = (j <= N_l) ? Z2[j] : 0.0;
-                        const double z1l = (j > 0 && j - 1 <= N_l) ? Z1[j - 1] : 0.0, z1r = (j + 1 <= N_l && j + 1 < WLa) ? Z1[j + 1] : 0.0;
-                        const double z2l = (j > 0 && j - 1 <= N_l) ? Z2[j - 1] : 0.0, z2r = (j + 1 <= N_l && j + 1 < WLa) ? Z2[j + 1] : 0.0;
-                        double pj = 0.0, pj1 = 0.0;
-                        if (coupled) {
-                            int i0, i1; double w0, w1;
-                            if (j <= N_l) { interp_row(s_lt, j, N_t, i0, i1, w0, w1); pj = w0 * qs[i0] + w1 * qs[i1]; }
-                            if (j + 1 <= N_l) { interp_row(s_lt, j + 1, N_t, i0, i1, w0, w1); pj1 = w0 * qs[i0] + w1 * qs[i1]; }
-                        }
-                        v = dB * z1c + eB * (z1l + z1r) + dC * z2c + eC * (z2l + z2r) - phi * ((pj1 - pj) * ihl);
+                for (int j = ln; j < WLp; j += L) {
+                    int i0 = 0, i1 = 0; float w0 = 0.f, w1 = 0.f;
+                    if (j <= N_l) {
+                        interp_row(s_lt, j, N_t, i0, i1, w0, w1);
+                        i0 = min(i0, LE - 1); i1 = min(i1, LE - 1);
                     }
-                    RL[j] = v;
+                    LW[2 * j] = (double)w0; LW[2 * j + 1] = (double)w1; LI[j] = i0 | (i1 << 16);
                 }
-                __syncwarp();
+                curNt = N_t; curNl = N_l;
+              }
+              __syncwarp();
             }
 
-            // ---- bow: raised-cosine weights over the Nx_t1-point axis (bow.cpp:32, misc.cpp:20-34) ----
-            double rc[ET];
-            double rc_extra = 0.0;
-            const double vB = t[T_VB], FB = t[T_FB];
-            if (do_bow) {
-                const double Nd = (double)NXT;
-                const double ctr = __ddiv_rn(__dmul_rn(t[T_XB], (double)(N_t - 1)), Nd);
-                const double wid = __ddiv_rn(__dmul_rn(__dmul_rn(t[T_WID], ht), (double)(N_t - 1)), Nd);
-                const double hw = wid * 0.5;
-                int ic = (int)floor((ctr - hw) * Nd) - 2;
-                ic = ic < 0 ? 0 : ic;
-                const int i = ic + ln;
-                double o = 0.0;
-                if (i < NXT) {
-                    const double x = (double)xaxs[i];
-                    const double dm = __dsub_rn(__dsub_rn(x, ctr), hw), dp = __dadd_rn(__dsub_rn(x, ctr), hw);
-                    const double p = __dmul_rn(-dm, dp);
-                    if (p > 0) o = 0.5 * (1 + cos(((2 * M_PI) * (x - ctr)) / wid));
-                    else if (p != p) o = p;
-                }
-                if (ln == L - 1 && o != 0.0) status |= SFDTD_ST_BOW_WINDOW;
-                const double S = red_sum<L>(fabs(o));
-                o = o / S;                               // 0/0 -> NaN like the reference
-                rc_extra = red_sum<L>((i >= L * ET && i < NXT) ? o : 0.0);
+            // ---- per-row coefficients, base right-hand side, factorisation ----
+            TriSolver<L, ET> ts;
+            double mu[ET + 1], rt[ET];
+            const int i0row = ln * ET;
+            {
+                double sq[ET + 1];
+                {
+                    // masked previous states (mask_1d, string.cpp:129-132): x * 0 keeps NaN like the reference's multiply
+                    double e1[ET + 4], e2[ET + 2];
 #pragma unroll
-                for (int r = 0; r < ET; r++) {
-                    const int w = ln * ET + r - ic;
-                    const double v = shix<L>(o, w & (L - 1));
-                    rc[r] = (w >= 0 && w < L) ? v : ((S == 0.0 || S != S) ? v * 0.0 : 0.0);
-                }
-            } else {
+                    for (int r = 0; r < ET + 4; r++) { const int i = i0row + r - 2; e1[r] = S[u1o + i] * ((i <= N_t) ? 1.0 : 0.0); }
 #pragma unroll
-                for (int r = 0; r < ET; r++) rc[r] = 0.0;
-            }
-
-            // ---- hammer: contact point and relative displacements (hammer.cpp:70-74) ----
-            const int idxH = (int)floor(__dmul_rn(xH, (double)(N_t - 1)));
-            double eta1 = 0.0, eta2 = 0.0, r1pow = 0.0;
-            if (do_ham) {
-                eta1 = uH1 - fetch_row<L, ET>(m1, idxH);
-                eta2 = uH2 - fetch_row<L, ET>(m2, idxH);
-                const double r1 = eta1 > 0 ? eta1 : (eta1 != eta1 ? eta1 : 0.0);
-                const double ex = aH - 1.0;
-                r1pow = (ex == 2.0) ? r1 * r1 : ((ex == 0.0) ? 1.0 : pow(r1, ex));
-            }
-
-            // ---- fixed-point loop over the forcing (string.cpp:200-258) ----
-            double uit[ET], nu[ET], xs[ET];
+                    for (int r = 0; r < ET + 2; r++) { const int i = i0row + r - 1; e2[r] = S[u2o + i] * ((i <= N_t) ? 1.0 : 0.0); }
+                    // Lambda = Dxb u1 (string.cpp:152) on the solved rows; mu = phi/h^2 Lambda; sq = phi/h^2 Lambda^2
+                    const double iht = t[T_IHT], ph2 = t[T_PH2];
 #pragma unroll
-            for (int r = 0; r < ET; r++) { uit[r] = u1[r]; xs[r] = m1[r]; nu[r] = 0.0; }
-            __syncwarp();      // all gathers of the staged 2 z1 + z2 are done before ZA is reused
-            for (int j = ln; j < WLp; j += L) { ZP[j] = Z1[j]; ZA[j] = (j <= N_l) ? Z1[j] : 0.0; }
-            __syncwarp();
-            int zc = 0;                       // current GS z buffer: 0 -> ZA, 1 -> ZB
-            double vrel = 0.0, FH = 0.0, uH = 0.0;
-            int iter = 0;
-            bool solved = false;
-            while (true) {
-                // bow force (bow.cpp:35-40)
-                double hb = 0.0;
-                if (do_bow) {
-                    double acc = 0.0;
+                    for (int r = 0; r <= ET; r++) {
+                        const int i = i0row + r;
+                        const double lam = (i < R) ? (e1[r + 2] - e1[r + 1]) * iht : 0.0;
+                        mu[r] = ph2 * lam; sq[r] = mu[r] * lam;
+                    }
+                    // B11 u1 + C11 u2  (string.cpp:223-224)
+                    const double diagB = t[T_DIAGB], off1B = t[T_OFF1B], kh4 = t[T_KH4], diagC = t[T_DIAGC], offC = t[T_OFFC];
 #pragma unroll
                     for (int r = 0; r < ET; r++) {
-                        const double dd = (iter == 0) ? (m1[r] - m2[r]) : (uit[r] - m1[r]);
-                        acc += rc[r] * (dd / kk - vB);
+                        const int i = i0row + r;
+                        double d4 = diagB;
+                        if (i == 1 || i == N_t - 1) d4 += kh4;          // Dxxxx_clamped (misc.cpp:146-163)
+                        const double Bu = d4 * e1[r + 2] + off1B * (e1[r + 1] + e1[r + 3]) + kh4 * (e1[r] + e1[r + 4]);
+                        const double Cu = diagC * e2[r + 1] + offC * (e2[r] + e2[r + 2]) + sq[r] * (e2[r + 1] - e2[r]) - sq[r + 1] * (e2[r + 2] - e2[r + 1]);
+                        rt[r] = Bu + Cu;
                     }
-                    vrel = red_sum<L>(acc) + rc_extra * (0.0 / kk - vB);
-                    const double sg = (vrel > 0) ? 1.0 : ((vrel < 0) ? -1.0 : 0.0);
-                    hb = (vrel != vrel) ? vrel : sg * (phi1 + (1 - phi1) * exp(-phi0 * fabs(vrel)));
                 }
-                // hammer loop (hammer.cpp:28-53), votes over the group
-                if (do_ham) {
-                    const double eps_u = fetch_row<L, ET>(uit, idxH);
-                    double eta_est = eta1 * hm;
-                    int hit = 0, more;
-                    do {
-                        const double eta = eta_est;
-                        const double fH = ((wpow * r1pow) * (eta + eta2)) / 2;
-                        FH = (eta1 > 0) ? fH : 0.0;
-                        double v = ((2 * uH1) - uH2) - k2 * FH;
-                        double tt = v - A.mhd;
-                        tt = tt > 0 ? tt : (tt != tt ? tt : 0.0);
-                        uH = tt + A.mhd;
-                        eta_est = (uH - eps_u) * hm;
-                        const int nc = fabs(eta - eta_est) > tol_t;
-                        hit++;
-                        more = group_has_hammer ? __syncthreads_or(valid && nc) : nc;
-                        if (hit >= A.max_iter) { if (more) status |= SFDTD_ST_HAMMER_CAP; more = 0; }
-                    } while (more);
-                    cnt_ham += hit;
-                }
-                // ---- linear solve  A w = -(RHS)  ----
-                const bool need = !solved || forced;
-                if (__any_sync(FULLMASK, need)) {
-                    double mr[ET];
-                    const double sB = -k2 * (FB * hb) * iht;
-                    const double sH = hamm ? nan0(-k2 * (Mr * FH)) : 0.0;
+                // K_tl (2 z1 + z2)  (B12 = 2 K_tl, C12 = K_tl); the first coupling guess z = 2 z1 - z2 goes to ZA
+                {
+                    double yy[ET];
 #pragma unroll
                     for (int r = 0; r < ET; r++) {
-                        const int i = ln * ET + r;
-                        double f = 0.0;
-                        if (bowm) f += nan0(sB * rc[r]);
-                        if (hamm && i == idxH) f += sH;
-                        mr[r] = (i < Wt && i < keep_flat) ? rt[r] + f : 0.0;
+                        const int j0 = tix[r] & 0xffff, j1 = tix[r] >> 16;
+                        const float w1f = twb[r];
+                        const double w1 = (double)w1f, w0 = (double)__fsub_rn(1.0f, w1f);
+                        yy[r] = w0 * (2.0 * Lb[z1o - 1 + j0] + Lb[z2o - 1 + j0]) + w1 * (2.0 * Lb[z1o - 1 + j1] + Lb[z2o - 1 + j1]);
                     }
-                    // block Gauss-Seidel: u <- A11^-1(-r_t - K_tl z) ; z <- Jacobi(A22, -r_l - K_lt u)
-                    bool conv = !need;
-                    int sweeps = 0;
-                    do {
-                        const bool act = !conv;
-                        const double *zcur = zc ? ZB : ZA;
-                        double *znew = zc ? ZA : ZB;
-                        double d[ET];
-                        {
-                            double y[ET];
+                    for (int j = ln; j < WLs; j += L) Lb[zao + j] = (j <= N_l) ? 2.0 * Lb[z1o + j] - Lb[z2o + j] : 0.0;
+                    double yyl = shup<L>(yy[ET - 1], 1);
+                    if (ln == 0) yyl = 0.0;
+                    double nub[ET + 1];
 #pragma unroll
-                            for (int r = 0; r < ET; r++) y[r] = coupled ? (double)tw0[r] * zcur[ti0[r]] + (double)tw1[r] * zcur[ti1[r]] : 0.0;
-                            double yl = shup<L>(y[ET - 1], 1);
-                            if (ln == 0) yl = 0.0;
-                            double q[ET + 1];
+                    for (int r = 0; r < ET; r++) nub[r] = mu[r] * (yy[r] - (r == 0 ? yyl : yy[r - 1]));
+                    nub[ET] = shdn<L>(nub[0], 1);
+                    if (ln == L - 1) nub[ET] = 0.0;
+                    const int Rk = tabi[jj * NI + I_RK];
 #pragma unroll
-                            for (int r = 0; r < ET; r++) q[r] = lam[r] * ((y[r] - (r == 0 ? yl : y[r - 1])) * iht);
-                            q[ET] = shdn<L>(q[0], 1);
-                            if (ln == L - 1) q[ET] = 0.0;
+                    for (int r = 0; r < ET; r++) rt[r] = (i0row + r < Rk) ? (rt[r] + (nub[r] - nub[r + 1])) : 0.0;
+                }
+                // A11 (string.cpp:153-162), rows < R, tail folded into row R-1
+                {
+                    const double offA = t[T_OFFA], diagA = t[T_DIAGA], corr = t[T_CORR];
+                    double ca[ET], cb[ET], cc[ET];
 #pragma unroll
-                            for (int r = 0; r < ET; r++) d[r] = -mr[r] + phi * ((q[r + 1] - q[r]) * iht);
+                    for (int r = 0; r < ET; r++) {
+                        const int i = i0row + r;
+                        const bool in = i < R;
+                        ca[r] = (in && i > 0) ? offA - sq[r] : 0.0;
+                        cc[r] = (i + 1 < R) ? offA - sq[r + 1] : 0.0;
+                        double bb = diagA + sq[r] + sq[r + 1];
+                        if (i == R - 1) bb -= corr;
+                        cb[r] = in ? bb : 1.0;
+                    }
+                    ts.factor(ca, cb, cc, ln);
+                }
+                // l-block base RHS, only when the flat-index mask leaves any of it (string.cpp:233)
+                const int keep_l = tabi[jj * NI + I_KEEPL];
+                if (__any_sync(FULLMASK, keep_l > 0)) {
+                    // q2 = mu Dxb u2 -> smem, then K_lt u2 by gathers
+#pragma unroll
+                    for (int r = 0; r < ET; r++) {
+                        const int i = i0row + r;
+                        const double a2 = S[u2o + i] * ((i <= N_t) ? 1.0 : 0.0), b2 = S[u2o + i - 1] * ((i - 1 <= N_t) ? 1.0 : 0.0);
+                        qs[i] = mu[r] * (a2 - b2);
+                    }
+                    __syncwarp();
+                    const double ihl = t[T_IHL], ihl2 = ihl * ihl, s0k = t[T_S0K], s1k = t[T_S1K], ga2 = t[T_GA2], phl = t[T_PHL];
+                    const double dB = -2 + 2 * ga2 * ihl2, eB = -ga2 * ihl2;
+                    const double dC = (1 - s0k) - 2 * s1k * ihl2, eC = s1k * ihl2;
+                    for (int j = ln; j < WLa; j += L) {
+                        double v = 0.0;
+                        if (j < keep_l && j < WLs) {
+                            const double z1c = (j <= N_l) ? Lb[z1o + j] : 0.0, z2c = (j <= N_l) ? Lb[z2o + j] : 0.0;
+                            const double z1l = (j - 1 <= N_l) ? Lb[z1o + j - 1] : 0.0, z1r = (j + 1 <= N_l) ? Lb[z1o + j + 1] : 0.0;
+                            const double z2l = (j - 1 <= N_l) ? Lb[z2o + j - 1] : 0.0, z2r = (j + 1 <= N_l) ? Lb[z2o + j + 1] : 0.0;
+                            const int li0 = LI[j], li1 = LI[j + 1];
+                            const double pj = LW[2 * j] * qs[li0 & 0xffff] + LW[2 * j + 1] * qs[li0 >> 16];
+                            const double pj1 = LW[2 * j + 2] * qs[li1 & 0xffff] + LW[2 * j + 3] * qs[li1 >> 16];
+                            v = dB * z1c + eB * (z1l + z1r) + dC * z2c + eC * (z2l + z2r) - phl * (pj1 - pj);
                         }
-                        ts.solve(d, ln);
-                        float du = 0.f, su = 0.f;
+                        Lb[rlo + j] = v;
+                    }
+                }
+                __syncwarp();
+            }
+
+            // ---- block Gauss-Seidel solve of  A w = -(mr ; RL)  -> xs (registers), zfo (offset of the final z) ----
+            double xs[ET];
+#pragma unroll
+            for (int r = 0; r < ET; r++) xs[r] = 0.0;
+            int zfo = z1o;
+            auto gs_solve = [&](const double (&mr)[ET], bool need, bool first) {
+                bool conv = !need;
+                int sweeps = 0;
+                float e_prev = 0.f, isu = 0.f, isz = 0.f;
+                int zco = first ? zao : zfo;
+                const int keep_l = tabi[jj * NI + I_KEEPL];
+                do {
+                    const bool act = !conv;
+                    const int zno = (zco == zao) ? zbo : zao;
+                    double d[ET];
+                    {
+                        double y[ET];
 #pragma unroll
                         for (int r = 0; r < ET; r++) {
-                            du = fmaxf(du, (float)fabs(d[r] - xs[r]));
-                            su = fmaxf(su, (float)fabs(d[r]));
-                            if (act) xs[r] = d[r];
+                            const int j0 = tix[r] & 0xffff, j1 = tix[r] >> 16;
+                            const float w1f = twb[r];
+                            y[r] = (double)__fsub_rn(1.0f, w1f) * Lb[zco - 1 + j0] + (double)w1f * Lb[zco - 1 + j1];
                         }
-                        float dz = 0.f, sz = 0.f;
-                        {
-                            double xl = shup<L>(xs[ET - 1], 1);
-                            if (ln == 0) xl = 0.0;
-                            if (act) {
+                        double yl = shup<L>(y[ET - 1], 1);
+                        if (ln == 0) yl = 0.0;
+                        double nuc[ET + 1];
 #pragma unroll
-                                for (int r = 0; r < ET; r++) qs[ln * ET + r] = lam[r] * ((xs[r] - (r == 0 ? xl : xs[r - 1])) * iht);
-                            }
-                            __syncwarp();
-                            if (act) {
-                                for (int j = ln; j < WLs; j += L) {
-                                    double pj = 0.0, pj1 = 0.0;
-                                    if (coupled) {
-                                        int i0, i1; double w0, w1;
-                                        if (j <= N_l) { interp_row(s_lt, j, N_t, i0, i1, w0, w1); pj = w0 * qs[i0] + w1 * qs[i1]; }
-                                        if (j + 1 <= N_l) { interp_row(s_lt, j + 1, N_t, i0, i1, w0, w1); pj1 = w0 * qs[i0] + w1 * qs[i1]; }
-                                    }
-                                    const double rhs = -((has_rl && j < keep_l) ? RL[j] : 0.0) + phi * ((pj1 - pj) * ihl);
-                                    const double zl = (j > 0) ? zcur[j - 1] : 0.0, zr = (j + 1 < WLs) ? zcur[j + 1] : 0.0;
-                                    const double zn = (rhs - eA * (zl + zr)) * idA;
-                                    dz = fmaxf(dz, (float)fabs(zn - zcur[j]));
-                                    sz = fmaxf(sz, (float)fabs(zn));
-                                    znew[j] = zn;
-                                }
-                                for (int j = WLs + ln; j < WLp; j += L) znew[j] = 0.0;
-                            }
-                            __syncwarp();
-                            if (act) zc ^= 1;
+                        for (int r = 0; r < ET; r++) nuc[r] = mu[r] * (y[r] - (r == 0 ? yl : y[r - 1]));
+                        nuc[ET] = shdn<L>(nuc[0], 1);
+                        if (ln == L - 1) nuc[ET] = 0.0;
+#pragma unroll
+                        for (int r = 0; r < ET; r++) d[r] = (nuc[r + 1] - nuc[r]) - mr[r];
+                    }
+                    ts.solve(d, ln);
+                    float du = 0.f, su = 0.f;
+#pragma unroll
+                    for (int r = 0; r < ET; r++) {
+                        du = fmaxf(du, absf_nan_inf(d[r] - xs[r]));
+                        if (sweeps == 0) su = fmaxf(su, absf_nan_inf(d[r]));
+                        if (act) xs[r] = d[r];
+                    }
+                    // q = mu (x_i - x_{i-1})  (the scale phi/h_t^2 and the 1/h_t of Dxb are folded into T_PHL)
+                    double xl = shup<L>(xs[ET - 1], 1);
+                    if (ln == 0) xl = 0.0;
+                    if (act) {
+#pragma unroll
+                        for (int r = 0; r < ET; r++) qs[i0row + r] = mu[r] * (xs[r] - (r == 0 ? xl : xs[r - 1]));
+                    }
+                    __syncwarp();
+                    if (act) {
+                        for (int j = ln; j <= WLs; j += L) {
+                            const int li = LI[j];
+                            const double2 w = *(const double2 *)(LW + 2 * j);
+                            Lb[po + j] = w.x * qs[li & 0xffff] + w.y * qs[li >> 16];
                         }
-                        du = red_maxf<L>(du); su = red_maxf<L>(su); dz = red_maxf<L>(dz); sz = red_maxf<L>(sz);
-                        sweeps++;
-                        bool ok = !(du > (float)GS_TOL * su) && !(dz > (float)GS_TOL * sz);
-                        if (!coupled && !has_rl) ok = true;              // uncoupled and no l-RHS: the first solve is exact
+                    }
+                    __syncwarp();
+                    float dz = 0.f, sz = 0.f;
+                    if (act) {
+                        const double PHL = t[T_PHL], idA = t[T_IDA], eidA = t[T_EIDA];
+                        for (int j = ln; j < WLs; j += L) {
+                            double rhs = PHL * (Lb[po + j + 1] - Lb[po + j]);
+                            if (j < keep_l) rhs -= Lb[rlo + j];
+                            const double zr = (j + 1 < WLs) ? Lb[zco + j + 1] : 0.0;
+                            const double zn = rhs * idA - eidA * (Lb[zco + j - 1] + zr);
+                            dz = fmaxf(dz, absf_nan_inf(zn - Lb[zco + j]));
+                            sz = fmaxf(sz, absf_nan_inf(zn));
+                            Lb[zno + j] = zn;
+                        }
+                    }
+                    __syncwarp();
+                    if (act) zco = zno;
+                    sweeps++;
+                    bool ok;
+                    if (sweeps == 1) {
+                        su = red_maxf<L>(su); sz = red_maxf<L>(sz);
+                        isu = 1.0f / su; isz = 1.0f / sz;          // 1/0 = inf: (0 * inf) = NaN is dropped by fmaxf below
+                        ok = false;
+                        if (!(su < INFINITY) || !(sz < INFINITY)) ok = true;      // NaN / inf state: nothing left to converge
+                    } else {
+                        // relative change of this sweep, both blocks; predicted error  e * rho / (1 - rho)
+                        float e = fmaxf(du * isu, dz * isz);
+                        e = red_maxf<L>(e);
+                        float rho = 2.0f * rho_h;
+                        if (sweeps >= 3 && e_prev > 0.f) {
+                            const float rr = e / e_prev;
+                            if (act) rho_h = (rr > rho_h) ? rr : 0.5f * (rho_h + rr);
+                            rho = 1.5f * rho_h;
+                        }
+                        rho = fminf(rho, 0.9f);
+                        const float est = e * rho / (1.0f - rho);
+                        const int minS = (keep_l > 0) ? 4 : 2;
+                        ok = (sweeps >= minS) && !(est > GS_TOL);
+                        if (!(e < INFINITY)) ok = true;
+                        e_prev = e;
                         if (act && sweeps >= GS_CAP && !ok) { status |= SFDTD_ST_SOLVER_CAP; ok = true; }
-                        if (act) { cnt_sweeps += 1; conv = ok; }
-                    } while (__any_sync(FULLMASK, !conv));
-                    solved = true;
+                    }
+                    if (act) { cnt_sweeps += 1; conv = ok; }
+                } while (__any_sync(FULLMASK, !conv));
+                if (need) zfo = zco;
+            };
+
+            double vrel = 0.0, FH = 0.0, uH = 0.0;
+            double nu[ET];
+
+            // ---- bow: raised-cosine weights over the Nx_t1-point axis (bow.cpp:32, misc.cpp:20-34) ----
+            // window rows bow_ic + c*L + ln (c = 0, 1); bow_o[c] = this lane's normalised weights; bow_S = normaliser
+            double bow_o[2] = {0.0, 0.0}, bow_S = 1.0; int bow_ic = 0;
+            auto bow_window = [&]() {
+                const double ctr = t[T_CTR], wid = t[T_WID];
+                const double hw = wid * 0.5;
+                bow_ic = tabi[jj * NI + I_IC];
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int i = bow_ic + c * L + ln;
+                    double o = 0.0;
+                    if (i < NXT) {
+                        const double x = (double)xaxs[i];
+                        const double dm = __dsub_rn(__dsub_rn(x, ctr), hw), dp = __dadd_rn(__dsub_rn(x, ctr), hw);
+                        const double p = __dmul_rn(-dm, dp);
+                        if (p > 0) o = 0.5 * (1 + cos(((2 * M_PI) * (x - ctr)) / wid));
+                        else if (p != p) o = p;
+                    }
+                    if (((c == 1 && ln == L - 1) || i >= LE) && o != 0.0) status |= SFDTD_ST_BOW_WINDOW;
+                    bow_o[c] = o; acc += fabs(o);
                 }
-                // ---- mask + Dirichlet (string.cpp:240-246), residuals (string.cpp:248-253) ----
-                int nc_t = 0, nan_u = 0;
+                bow_S = red_sum<L>(acc);
+                bow_o[0] = bow_o[0] / bow_S; bow_o[1] = bow_o[1] / bow_S;      // 0/0 -> NaN like the reference
+            };
+            const double ik = A.ik, k2 = A.k2;
+
+            if (!GROUPED) {
+                // ================= independent mode: unforced string, one solve =================
+                gs_solve(rt, true, true);
+                cnt_outer += 2;      // the reference's second pass reproduces the first (residual 0)
 #pragma unroll
                 for (int r = 0; r < ET; r++) {
-                    const int i = ln * ET + r;
-                    const bool keep = (i <= N_t) && (i != 0) && (i != N_t) && (i < Wt);
+                    const int i = i0row + r;
+                    const bool keep = (i < N_t) && (i != 0) && (i < R);
                     nu[r] = keep ? xs[r] : xs[r] * 0.0;
-                    const double df = fabs(uit[r] - nu[r]);
-                    nan_u |= (df != df);
-                    nc_t |= (df > tol_t);
-                    uit[r] = nu[r];
                 }
-                const double *zsol = zc ? ZB : ZA;
-                int nc_l = 0, nan_z = 0;
-                for (int j = ln; j < WLp; j += L) {
-                    const bool keep = (j <= N_l) && (j != 0) && (j != N_l) && (j < WLs);
-                    const double zv = keep ? zsol[j] : zsol[j] * 0.0;
-                    const double df = fabs(ZP[j] - zv);
-                    nan_z |= (df != df);
-                    nc_l |= (df > tol_l);
-                    ZP[j] = zv;
+                if (do_bow) {
+                    // v_rel of the last pass (bow.cpp:35-38): sum rc_i ((u_i - u1_i)/k - v_b) over the window rows
+                    bow_window();
+#pragma unroll
+                    for (int r = 0; r < ET; r++) { const int i = i0row + r; qs[i] = nu[r] - S[u1o + i] * ((i <= N_t) ? 1.0 : 0.0); }
+                    __syncwarp();
+                    const int wi0 = min(bow_ic + ln, LE - 1), wi1 = min(bow_ic + L + ln, LE - 1);
+                    const double vB = t[T_VB];
+                    vrel = red_sum<L>(bow_o[0] * (qs[wi0] * ik - vB) + bow_o[1] * (qs[wi1] * ik - vB));
+                    __syncwarp();
                 }
+                if (do_ham) {
+                    // un-hammered string: the contact loop runs once with eta = 0 (hammer.cpp:28-53)
+                    const int idxH = tabi[jj * NI + I_IDXH];
+                    const double mk = (idxH <= N_t) ? 1.0 : 0.0;
+                    const double eta1 = uH1 - S[u1o + idxH] * mk;
+                    const double eta2 = uH2 - S[u2o + idxH] * mk;
+                    const double r1 = eta1 > 0 ? eta1 : (eta1 != eta1 ? eta1 : 0.0);
+                    const double ex = cst[C_AHM1];
+                    const double r1pow = (ex == 2.0) ? r1 * r1 : ((ex == 0.0) ? 1.0 : pow(r1, ex));
+                    const double fH = ((cst[C_WPOW] * r1pow) * (0.0 + eta2)) / 2;
+                    FH = (eta1 > 0) ? fH : 0.0;
+                    double tt = (((2 * uH1) - uH2) - k2 * FH) - A.mhd;
+                    tt = tt > 0 ? tt : (tt != tt ? tt : 0.0);
+                    uH = tt + A.mhd;
+                    cnt_ham += 2;
+                }
+            } else {
+                // ================= grouped mode: fixed-point loop over the forcing (string.cpp:200-258) =================
+                const double hm = hamm ? 1.0 : 0.0;
+                const int idxH = tabi[jj * NI + I_IDXH];
+                const int Rk = tabi[jj * NI + I_RK];
+                bool rc_nan = false;
+                if (do_bow) {
+                    bow_window();
+                    rc_nan = (bow_S == 0.0) || (bow_S != bow_S);             // every weight is NaN (0/0) in the reference
+#pragma unroll
+                    for (int r = 0; r < ET; r++) RC[i0row + r] = 0.0;
+                    __syncwarp();
+                    if (bow_ic + ln < LE) RC[bow_ic + ln] = bow_o[0];
+                    if (bow_ic + L + ln < LE) RC[bow_ic + L + ln] = bow_o[1];
+                    __syncwarp();
+                }
+                // hammer: contact point and relative displacements (hammer.cpp:70-74)
+                double eta1 = 0.0, eta2 = 0.0, r1pow = 0.0;
+                if (do_ham) {
+                    const double mk = (idxH <= N_t) ? 1.0 : 0.0;
+                    eta1 = uH1 - S[u1o + idxH] * mk;
+                    eta2 = uH2 - S[u2o + idxH] * mk;
+                    const double r1 = eta1 > 0 ? eta1 : (eta1 != eta1 ? eta1 : 0.0);
+                    const double ex = cst[C_AHM1];
+                    r1pow = (ex == 2.0) ? r1 * r1 : ((ex == 0.0) ? 1.0 : pow(r1, ex));
+                }
+                const double tol_t = t[T_TOLT], tol_l = t[T_TOLL];
+                // the iterate starts as the unmasked state[n-1] (string.cpp:190-191)
+#pragma unroll
+                for (int r = 0; r < ET; r++) nu[r] = S[u1o + i0row + r];
+                for (int j = ln; j < WLa; j += L) Lb[zpo + j] = Lb[z1o + j];
                 __syncwarp();
-                nan_u = red_or<L>(nan_u); nan_z = red_or<L>(nan_z);
-                nc_t = red_or<L>(nc_t);
-                nc_l = red_or<L>(nc_l);
-                const int not_conv = (nc_t && !nan_u) || (nc_l && !nan_z);
-                iter++;
-                int more = __syncthreads_or(valid && not_conv);
-                if (iter >= A.max_iter) { if (more) status |= SFDTD_ST_OUTER_CAP; more = 0; }
-                if (!more) break;
+                int iter = 0;
+                bool solved = false;
+                while (true) {
+                    // bow force (bow.cpp:35-40)
+                    double hb = 0.0;
+                    if (do_bow) {
+                        const double vB = t[T_VB];
+                        double acc = 0.0;
+#pragma unroll
+                        for (int r = 0; r < ET; r++) {
+                            const int i = i0row + r;
+                            const double mk = (i <= N_t) ? 1.0 : 0.0;
+                            const double m1 = S[u1o + i] * mk;
+                            const double dd = (iter == 0) ? (m1 - S[u2o + i] * mk) : (nu[r] - m1);
+                            const double rcv = rc_nan ? bow_o[0] : RC[i];
+                            acc += rcv * (dd * ik - vB);
+                        }
+                        vrel = red_sum<L>(acc);
+                        const double sg = (vrel > 0) ? 1.0 : ((vrel < 0) ? -1.0 : 0.0);
+                        const double phi0 = cst[C_PHI0], phi1 = cst[C_PHI1];
+                        hb = (vrel != vrel) ? vrel : sg * (phi1 + (1 - phi1) * exp(-phi0 * fabs(vrel)));
+                    }
+                    // hammer loop (hammer.cpp:28-53), votes over the group
+                    if (do_ham) {
+                        const double eps_u = fetch_row<L, ET>(nu, idxH);
+                        const double wpow = cst[C_WPOW];
+                        double eta_est = eta1 * hm;
+                        int hit = 0, more;
+                        do {
+                            const double eta = eta_est;
+                            const double fH = ((wpow * r1pow) * (eta + eta2)) / 2;
+                            FH = (eta1 > 0) ? fH : 0.0;
+                            double v = ((2 * uH1) - uH2) - k2 * FH;
+                            double tt = v - A.mhd;
+                            tt = tt > 0 ? tt : (tt != tt ? tt : 0.0);
+                            uH = tt + A.mhd;
+                            eta_est = (uH - eps_u) * hm;
+                            const int nc = fabs(eta - eta_est) > tol_t;
+                            hit++;
+                            more = group_has_hammer ? __syncthreads_or(valid && nc) : nc;
+                            if (hit >= A.max_iter) { if (more) status |= SFDTD_ST_HAMMER_CAP; more = 0; }
+                        } while (more);
+                        cnt_ham += hit;
+                    }
+                    // ---- linear solve  A w = -(RHS)  ----
+                    const bool need = !solved || forced;
+                    if (__any_sync(FULLMASK, need)) {
+                        double mr[ET];
+                        const double sB = -k2 * (t[T_FB] * hb) * t[T_IHT];
+                        const double sH = hamm ? nan0(-k2 * (cst[C_MR] * FH)) : 0.0;
+#pragma unroll
+                        for (int r = 0; r < ET; r++) {
+                            const int i = i0row + r;
+                            double f = 0.0;
+                            if (bowm) f += nan0(sB * (rc_nan ? bow_o[0] : RC[i]));
+                            if (hamm && i == idxH) f += sH;
+                            mr[r] = (i < Rk) ? rt[r] + f : 0.0;
+                        }
+                        gs_solve(mr, need, !solved);
+                        solved = true;
+                    }
+                    // ---- mask + Dirichlet (string.cpp:240-246), residuals (string.cpp:248-253) ----
+                    int nc_t = 0, nan_u = 0;
+#pragma unroll
+                    for (int r = 0; r < ET; r++) {
+                        const int i = i0row + r;
+                        const bool keep = (i < N_t) && (i != 0) && (i < R);
+                        const double nv = keep ? xs[r] : xs[r] * 0.0;
+                        const double df = fabs(nu[r] - nv);
+                        nan_u |= (df != df);
+                        nc_t |= (df > tol_t);
+                        nu[r] = nv;
+                    }
+                    int nc_l = 0, nan_z = 0;
+                    for (int j = ln; j < WLa; j += L) {
+                        const bool keep = (j < N_l) && (j != 0) && (j < WLs);
+                        const double zs = (j < WLs) ? Lb[zfo + j] : 0.0;
+                        const double zv = keep ? zs : zs * 0.0;
+                        const double df = fabs(Lb[zpo + j] - zv);
+                        nan_z |= (df != df);
+                        nc_l |= (df > tol_l);
+                        Lb[zpo + j] = zv;
+                    }
+                    __syncwarp();
+                    nan_u = red_or<L>(nan_u); nan_z = red_or<L>(nan_z);
+                    nc_t = red_or<L>(nc_t);
+                    nc_l = red_or<L>(nc_l);
+                    const int not_conv = (nc_t && !nan_u) || (nc_l && !nan_z);
+                    iter++;
+                    int more = __syncthreads_or(valid && not_conv);
+                    if (iter >= A.max_iter) { if (more) status |= SFDTD_ST_OUTER_CAP; more = 0; }
+                    if (!more) break;
+                }
+                cnt_outer += iter;
             }
-            cnt_outer += iter; cnt_steps += 1;
+            cnt_steps += 1;
 
             // ---- save and readout (string.cpp:263-303) ----
             double uo, zo;
-            if (surf) {
-                const double rw = 0.5 * ht;
-                const double wgt = rw * 1.0 + rw * hm + rw * bm;
-                double acc = 0.0;
-#pragma unroll
-                for (int r = 0; r < ET; r++) acc += ((nu[r] - u1[r]) * wgt) / kk;
-                uo = red_sum<L>(acc);
-                acc = 0.0;
-                for (int j = ln; j < WLp; j += L) acc += ((ZP[j] - Z1[j]) * wgt) / kk;
-                zo = red_sum<L>(acc);
-            } else {
-                const int ui = 1 + (int)floor(__dmul_rn((double)N_t, rp));
-                const double uf = 1 + rp / ht - (double)ui;
-                const int zi = 1 + (int)floor(__dmul_rn((double)N_l, rp));
-                const double zf = 1 + rp / t[T_HL] - (double)zi;
-                const double ua = fetch_row<L, ET>(nu, ui), ub = fetch_row<L, ET>(nu, ui + 1);
-                uo = (1 - uf) * ua + uf * ub;
-                const double za = (zi < WLp) ? ZP[zi] : 0.0, zb = (zi + 1 < WLp) ? ZP[zi + 1] : 0.0;
-                zo = (1 - zf) * za + zf * zb;
-            }
-            // state rows: state[:, n] += u  (in place, onto pre-loaded content; string.cpp:264-265)
             {
-                double *su = (double *)a.state_u.ptr + (int64_t)b * a.state_u.bs + (int64_t)n * a.state_u.ts;
+                // new longitudinal row (masked, Dirichlet) into the oldest buffer; surface integral on the fly
+                const int zno = z2o;
+                const double rdw = t[T_RDW];
+                double acc = 0.0;
+                const int hi = max(max(ext1, ext2), WLs);
+                if (GROUPED) {
+                    for (int j = ln; j < hi; j += L) { const double zv = Lb[zpo + j]; acc += (zv - Lb[z1o + j]) * rdw; Lb[zno + j] = zv; }
+                } else {
+                    for (int j = ln; j < hi; j += L) {
+                        const bool keep = (j < N_l) && (j != 0) && (j < WLs);
+                        const double zs = (j < WLs) ? Lb[zfo + j] : 0.0;
+                        const double zv = keep ? zs : zs * 0.0;
+                        acc += (zv - Lb[z1o + j]) * rdw; Lb[zno + j] = zv;
+                    }
+                }
+                ext2 = ext1; ext1 = WLs;
+                if (surf) {
+                    zo = red_sum<L>(acc);
+                    double au = 0.0;
 #pragma unroll
-                for (int r = 0; r < ET; r++) {
-                    const int i = ln * ET + r;
-                    double row = nu[r];
-                    if (save_state && i < NXT) { row += su[i]; if (valid) su[i] = row; }
-                    u2[r] = u1[r]; u1[r] = row;
+                    for (int r = 0; r < ET; r++) au += (nu[r] - S[u1o + i0row + r]) * rdw;
+                    uo = red_sum<L>(au);
+                } else {
+                    __syncwarp();
+                    const double rp = cst[C_RP];
+                    const int ui = 1 + (int)floor(__dmul_rn((double)N_t, rp));
+                    const double uf = 1 + rp * t[T_IHT] - (double)ui;
+                    const int zi = 1 + (int)floor(__dmul_rn((double)N_l, rp));
+                    const double zf = 1 + rp * t[T_IHL] - (double)zi;
+                    const double ua = fetch_row<L, ET>(nu, ui), ub = fetch_row<L, ET>(nu, ui + 1);
+                    uo = (1 - uf) * ua + uf * ub;
+                    const double za = (zi < WLa) ? Lb[zno + zi] : 0.0, zb = (zi + 1 < WLa) ? Lb[zno + zi + 1] : 0.0;
+                    zo = (1 - zf) * za + zf * zb;
                 }
-                double *sz = (double *)a.state_z.ptr + (int64_t)b * a.state_z.bs + (int64_t)n * a.state_z.ts;
-                double *Zn = Z2;                       // recycle the oldest row buffer
-                for (int j = ln; j < WLp; j += L) {
-                    double row = ZP[j];
-                    if (save_state && j < NXL && j < WLa) { row += sz[j]; if (valid) sz[j] = row; }
-                    Zn[j] = row;
+                // state rows: state[:, n] += u  (in place, onto pre-loaded content; string.cpp:264-265)
+                if (save_state) {
+                    double *su = (double *)a.state_u.ptr + (int64_t)b * a.state_u.bs + (int64_t)n * a.state_u.ts;
+#pragma unroll
+                    for (int r = 0; r < ET; r++) {
+                        const int i = i0row + r;
+                        if (i < NXT) { nu[r] += su[i]; if (valid) su[i] = nu[r]; }
+                    }
+                    double *sz = (double *)a.state_z.ptr + (int64_t)b * a.state_z.bs + (int64_t)n * a.state_z.ts;
+                    __syncwarp();
+                    for (int j = ln; j < WLa; j += L) {
+                        if (j < NXL) { const double row = Lb[zno + j] + sz[j]; if (valid) sz[j] = row; Lb[zno + j] = row; }
+                    }
+                    ext1 = WLa;
                 }
-                Z2 = Z1; Z1 = Zn;
+#pragma unroll
+                for (int r = 0; r < ET; r++) S[u2o + i0row + r] = nu[r];
+                { const int tmp = u1o; u1o = u2o; u2o = tmp; }
+                z2o = z1o; z1o = zno;
                 __syncwarp();
             }
             const double uHtot = t[T_UHPRE] + (out_ham ? uH : 0.0);
             uH2 = uH1; uH1 = uHtot;
-            sig0_last = t[T_SIG0]; sig1_last = t[T_SIG1];
             if (ln == 0) {
-                double *o = ost + jj * (NOUT + 1);
+                double *o = ost + jj * NOUT;
                 o[0] = uo; o[1] = zo; o[2] = out_bow ? vrel : 0.0; o[3] = out_ham ? FH : 0.0; o[4] = uHtot;
             }
         }
-        // ---- flush staged outputs: lane j writes step n0+j (coalesced rows) ----
+        // ---- flush staged outputs: lane s writes step n0+s (coalesced rows) ----
         __syncwarp();
-        if (valid && ln < jmax) {
-            const int n = n0 + ln;
-            const double *o = ost + ln * (NOUT + 1);
-            ((double *)a.uout.ptr)[(int64_t)b * a.uout.bs + (int64_t)n * a.uout.ts] = o[0];
-            ((double *)a.zout.ptr)[(int64_t)b * a.zout.bs + (int64_t)n * a.zout.ts] = o[1];
-            ((double *)a.v_r.ptr)[(int64_t)b * a.v_r.bs + (int64_t)n * a.v_r.ts] = o[2];
-            ((double *)a.F_H.ptr)[(int64_t)b * a.F_H.bs + (int64_t)n * a.F_H.ts] = o[3];
-            ((double *)a.u_H.ptr)[(int64_t)b * a.u_H.bs + (int64_t)n * a.u_H.ts] = o[4];
-            ((double *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)n * a.u_H_out.ts] = o[4] / kk;
+        if (valid) {
+            const double ik = A.ik;
+            for (int s = ln; s < jmax; s += L) {
+                const int n = n0 + s;
+                const double *o = ost + s * NOUT;
+                ((double *)a.uout.ptr)[(int64_t)b * a.uout.bs + (int64_t)n * a.uout.ts] = o[0];
+                ((double *)a.zout.ptr)[(int64_t)b * a.zout.bs + (int64_t)n * a.zout.ts] = o[1];
+                ((double *)a.v_r.ptr)[(int64_t)b * a.v_r.bs + (int64_t)n * a.v_r.ts] = o[2];
+                ((double *)a.F_H.ptr)[(int64_t)b * a.F_H.bs + (int64_t)n * a.F_H.ts] = o[3];
+                ((double *)a.u_H.ptr)[(int64_t)b * a.u_H.bs + (int64_t)n * a.u_H.ts] = o[4];
+                ((double *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)n * a.u_H_out.ts] = o[4] * ik;
+            }
         }
-        __syncthreads();
+        __syncwarp();
     }
 
     // ---- epilogue ----
@@ -783,17 +1047,33 @@ __global__ void __launch_bounds__(MAXT, 1) sfdtd_step_kernel(const __grid_consta
 #pragma unroll
             for (int r = 0; r < ET; r++) {
                 const int i = ln * ET + r;
-                if (i < NXT) { su[i] = u2[r]; su[a.state_u.ts + i] = u1[r]; }
+                if (i < NXT) { su[i] = S[u2o + i]; su[a.state_u.ts + i] = S[u1o + i]; }
             }
             double *sz = (double *)a.state_z.ptr + (int64_t)b * a.state_z.bs;
-            for (int j = ln; j < WLp; j += L) if (j < NXL && j < WLa) { sz[j] = Z2[j]; sz[a.state_z.ts + j] = Z1[j]; }
+            for (int j = ln; j < WLa; j += L) if (j < NXL) { sz[j] = Lb[z2o + j]; sz[a.state_z.ts + j] = Lb[z1o + j]; }
         }
         // u_H_out / u_H columns 0,1 (simulator.cpp:57 divides the whole tensor)
         if (ln < 2 && ln < Nt) {
-            ((double *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)ln * a.u_H_out.ts] = ldx(a.u_H, b, ln) / kk;
+            ((double *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)ln * a.u_H_out.ts] = ldx(a.u_H, b, ln) * A.ik;
         }
         if (ln == 0) {
-            if (Nt > 2) { ((double *)a.sig0)[b] = sig0_last; ((double *)a.sig1)[b] = sig1_last; }
+            if (Nt > 2) {
+                // loss parameters of the last step (string.cpp:119-120)
+                const Derived d = derive(ldx(a.f0, b, Nt - 1), lds(a.kappa, b), lds(a.alpha, b), A);
+                const double *T60 = (const double *)a.T60.ptr + (int64_t)b * a.T60.bs;
+                const double T00 = T60[0], T01 = T60[1], T10 = T60[2], T11 = T60[3];
+                const double g2 = d.gamma * d.gamma, g4 = g2 * g2;
+                double z1, z2;
+                if (d.K > 0) {
+                    const double w1 = (2 * M_PI) * T00, w2 = (2 * M_PI) * T10;
+                    z1 = -g2 + sqrt(g4 + (4 * (d.K * d.K)) * (w1 * w1));
+                    z2 = -g2 + sqrt(g4 + (4 * (d.K * d.K)) * (w2 * w2));
+                } else { z1 = (T00 * T00) / g2; z2 = (T10 * T10) / g2; }
+                const bool m = (T00 * T01 * T10 * T11) != 0;
+                const double s0 = m ? (-z2 / T01 + z1 / T11) : 0.0, s1 = m ? (1 / T01 - 1 / T11) : 0.0;
+                const double c6 = 13.815510557964274;
+                ((double *)a.sig0)[b] = (c6 * s0) / (z1 - z2); ((double *)a.sig1)[b] = (c6 * s1) / (z1 - z2);
+            }
             if (a.status) a.status[b] = status_all;
             if (a.counters) {
                 a.counters[4 * b + 0] = cnt_outer; a.counters[4 * b + 1] = cnt_sweeps;
@@ -802,6 +1082,7 @@ __global__ void __launch_bounds__(MAXT, 1) sfdtd_step_kernel(const __grid_consta
         }
     }
 }
+
 
 // ---- FMA-pipe peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has no FP64/FP32 FMA figure) ----
 template <typename T>
@@ -825,23 +1106,43 @@ __global__ void __launch_bounds__(256) sfdtd_fma_peak_kernel(T *out, int iters, 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 
-struct Config { int L, ET, MAXT; void (*kern)(const KArgs); };
-#define CFG(L_, ET_, MT_) Config{L_, ET_, MT_, sfdtd_step_kernel<L_, ET_, MT_>}
-// smallest first; a group needs  W_t <= L*ET  and  ceil32(G*L) <= MAXT
+struct Config { int L, ET, maxt; bool grouped; void (*kern)(const KArgs); };
+#define CFG_I(L_, ET_, MB_) Config{L_, ET_, 128, false, sfdtd_step_kernel<L_, ET_, false, 128, MB_>}
+#define CFG_G(L_, ET_, MT_) Config{L_, ET_, MT_, true, sfdtd_step_kernel<L_, ET_, true, MT_, 1>}
+// smallest first.  independent mode: 128-thread CTAs, a string needs rows <= L*ET.
+// grouped mode: one CTA per group, needs rows <= L*ET and ceil32(G*L) <= maxt.
 const Config g_configs[] = {
-    CFG(16, 6, 128), CFG(16, 6, 384), CFG(16, 6, 1024),
-    CFG(32, 4, 256), CFG(32, 4, 1024),
-    CFG(32, 8, 128), CFG(32, 8, 512),
+    CFG_I(8, 4, 3), CFG_I(8, 6, 2), CFG_I(16, 4, 3), CFG_I(16, 6, 2), CFG_I(32, 4, 3), CFG_I(32, 8, 1),
+    CFG_G(8, 4, 256), CFG_G(8, 6, 256), CFG_G(16, 4, 512), CFG_G(16, 6, 384), CFG_G(32, 4, 1024), CFG_G(32, 8, 128), CFG_G(32, 8, 512),
 };
 constexpr int N_CONFIGS = sizeof(g_configs) / sizeof(g_configs[0]);
 
-size_t smem_bytes(const Config &c, int nslots, int NXT, size_t lblk_doubles) {
-    const int TB = c.L;
-    size_t bytes = sizeof(int) * ((nslots + 2) + 2 * TB * nslots + 2 * TB) + sizeof(float) * NXT;
-    bytes = (bytes + 7) / 8 * 8;
-    bytes += sizeof(double) * ((size_t)nslots * TB * NV + (size_t)nslots * TB * (NOUT + 1) + (size_t)nslots * (c.L * c.ET + 2) + lblk_doubles);
-    return bytes + 64;
+// longitudinal allocation classes of the independent mode (rows incl. the two guards)
+int wl_class(int rows) {
+    int c = 16;
+    while (c < rows) c *= 2;
+    return c;
 }
+
+size_t xax_doubles(int NXT, bool need_xax) { return need_xax ? (size_t)((NXT + 3) / 4) * 2 : 0; }
+
+// independent mode: nslots strings with WLp longitudinal rows each
+size_t smem_bytes_indep(const Config &c, int nslots, int NXT, int WLp, bool need_xax) {
+    const size_t dbl = xax_doubles(NXT, need_xax) + (size_t)nslots * (slot_fixed_doubles(c.L, c.ET, false) + slot_long_doubles(WLp, false));
+    return dbl * sizeof(double) + 16;
+}
+
+int kernel_regs(const Config &c) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, c.kern) != cudaSuccess) { cudaGetLastError(); return 255; }
+    return fa.numRegs;
+}
+
+// side streams so that the launches of different buckets overlap
+std::mutex g_stream_mu;
+std::vector<cudaStream_t> g_side_streams;
+std::vector<cudaEvent_t> g_side_events;
+cudaEvent_t g_fork_event = nullptr;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "%s: %s", #x, cudaGetErrorString(e_)); rc = SFDTD_ERR_CUDA; goto done; } } while (0)
 
@@ -897,17 +1198,19 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
 
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     int rc = SFDTD_OK;
-    int32_t *d_max = nullptr, *d_gids = nullptr;
-    std::vector<int32_t> h_max(2 * (size_t)a.B);
     const int n_groups = (a.B + a.group_size - 1) / a.group_size;
-    std::map<int, std::vector<int32_t>> buckets;      // config index -> group ids
-    std::map<int, size_t> bucket_smem;
-    std::vector<int32_t> h_gids;
+    int32_t *d_max = nullptr, *d_ids = nullptr, *d_wtab = nullptr;
+    std::vector<int32_t> h_max(2 * (size_t)a.B);
+    std::vector<uint8_t> h_bow(a.B), h_ham(a.B);
+    struct Bucket { std::vector<int32_t> ids; size_t smem = 0; };
+    std::map<std::pair<int, int>, Bucket> buckets;      // (config index, WLp) -> items
+    std::vector<int32_t> h_ids;
+    const bool skip_aux = a.flags & SFDTD_SKIP_AUX;
 
     KArgs K;
     memset(&K, 0, sizeof K);
     K.a = a;
-    K.k = (double)a.k; K.k2 = pow((double)a.k, 2.); K.k4 = pow((double)a.k, 4.);
+    K.k = (double)a.k; K.ik = 1.0 / (double)a.k; K.k2 = pow((double)a.k, 2.); K.k4 = pow((double)a.k, 4.);
     K.th = (double)a.theta_t;
     { const float om = 1 - a.theta_t; K.omth = (double)om; }                 // float32 (string.cpp:148)
     { const float t1 = 2 * a.theta_t - 1; const float t2 = 2 * t1; K.tt1 = (double)t1; K.tt2 = (double)t2; }   // string.cpp:30-31
@@ -916,63 +1219,122 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     K.max_iter = a.max_iter > 0 ? a.max_iter : 1000;
 
     CK(cudaMalloc(&d_max, sizeof(int32_t) * 2 * (size_t)a.B));
-    K.maxNt = d_max; K.maxNl = d_max + a.B;
+    CK(cudaMalloc(&d_wtab, sizeof(int32_t) * (size_t)n_groups * a.Nt));
     sfdtd_prepass_kernel<<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B);
     g_launches++;
     CK(cudaGetLastError());
+    sfdtd_width_kernel<<<dim3((a.Nt + 127) / 128, n_groups), 128, 0, stream>>>(K, d_wtab);
+    g_launches++;
+    CK(cudaGetLastError());
+    K.Wtab = d_wtab; K.maxNl = d_max + a.B;
     CK(cudaMemcpyAsync(h_max.data(), d_max, sizeof(int32_t) * 2 * (size_t)a.B, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h_bow.data(), a.bow_mask, a.B, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h_ham.data(), a.hammer_mask, a.B, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
 
     for (int g = 0; g < n_groups; g++) {
         const int g0 = g * a.group_size, G = std::min(a.group_size, a.B - g0);
-        int Wt = 0; size_t lblk = 0;
+        bool forced = false;
+        int Wt = 0, rows_g = 0;
         for (int s = 0; s < G; s++) {
+            forced = forced || h_bow[g0 + s] || h_ham[g0 + s];
             Wt = std::max(Wt, h_max[g0 + s] + 1);
-            lblk += 6 * (size_t)(h_max[a.B + g0 + s] + 1 + WL_MARGIN + 2);
         }
-        int pick = -1;
-        for (int c = 0; c < N_CONFIGS && pick < 0; c++) {
-            const Config &cf = g_configs[c];
-            const int threads = (a.group_size * cf.L + 31) / 32 * 32;
-            if (Wt <= cf.L * cf.ET && threads <= cf.MAXT) pick = c;
+        for (int s = 0; s < G; s++) {
+            // rows a string can need: its own N_t + 3 (+ the bow window of a bowed string), never more than W_t
+            const int rows = std::min(Wt, h_max[g0 + s] + 3 + (h_bow[g0 + s] ? 8 : 0));
+            if (!forced) {
+                int pick = -1;
+                for (int c = 0; c < N_CONFIGS && pick < 0; c++)
+                    if (!g_configs[c].grouped && rows <= g_configs[c].L * g_configs[c].ET) pick = c;
+                if (pick < 0) {
+                    snprintf(g_err, sizeof g_err, "string %d: %d transverse rows are outside the built kernel set", g0 + s, rows);
+                    rc = SFDTD_ERR_UNSUPPORTED; goto done;
+                }
+                buckets[{pick, wl_class(long_rows(h_max[a.B + g0 + s]))}].ids.push_back(g0 + s);
+            }
+            rows_g = std::max(rows_g, rows);
         }
-        if (pick < 0) {
-            snprintf(g_err, sizeof g_err, "group %d: W_t=%d with %d strings is outside the built kernel set", g, Wt, G);
-            rc = SFDTD_ERR_UNSUPPORTED; goto done;
+        if (forced) {
+            int pick = -1;
+            for (int c = 0; c < N_CONFIGS && pick < 0; c++) {
+                const Config &cf = g_configs[c];
+                const int threads = (a.group_size * cf.L + 31) / 32 * 32;
+                if (cf.grouped && rows_g <= cf.L * cf.ET && threads <= cf.maxt) pick = c;
+            }
+            if (pick < 0) {
+                snprintf(g_err, sizeof g_err, "group %d: %d transverse rows with %d strings is outside the built kernel set", g, rows_g, G);
+                rc = SFDTD_ERR_UNSUPPORTED; goto done;
+            }
+            // shared memory of this group's CTA: fixed slots + the strings' own longitudinal blocks
+            const Config &cf = g_configs[pick];
+            const int threads = (a.group_size * cf.L + 31) / 32 * 32, nslots = threads / cf.L;
+            size_t dbl = xax_doubles(a.Nx_t1, true) + (size_t)nslots * slot_fixed_doubles(cf.L, cf.ET, true) + (size_t)(nslots + 2) / 2 + 2;
+            for (int s = 0; s < nslots; s++) dbl += slot_long_doubles(long_rows(h_max[a.B + g0 + std::min(s, G - 1)]), true);
+            Bucket &bk = buckets[{pick, 0}];
+            bk.ids.push_back(g);
+            bk.smem = std::max(bk.smem, dbl * sizeof(double) + 16);
         }
-        const Config &cf = g_configs[pick];
-        const int threads = (a.group_size * cf.L + 31) / 32 * 32;
-        // spare slots shadow the last string: account for their l-blocks too
-        const int nslots = threads / cf.L;
-        const size_t last = 6 * (size_t)(h_max[a.B + g0 + G - 1] + 1 + WL_MARGIN + 2);
-        const size_t sm = smem_bytes(cf, nslots, a.Nx_t1, lblk + (size_t)(nslots - G) * last);
-        if (sm > 227 * 1024) {
-            snprintf(g_err, sizeof g_err, "group %d needs %zu bytes of shared memory (> 227 KB)", g, sm);
-            rc = SFDTD_ERR_UNSUPPORTED; goto done;
-        }
-        buckets[pick * 4096 + threads].push_back(g);
-        bucket_smem[pick * 4096 + threads] = std::max(bucket_smem[pick * 4096 + threads], sm);
     }
-    for (auto &kv : buckets) h_gids.insert(h_gids.end(), kv.second.begin(), kv.second.end());
-    CK(cudaMalloc(&d_gids, sizeof(int32_t) * h_gids.size()));
-    CK(cudaMemcpyAsync(d_gids, h_gids.data(), sizeof(int32_t) * h_gids.size(), cudaMemcpyHostToDevice, stream));
+    for (auto &kv : buckets) h_ids.insert(h_ids.end(), kv.second.ids.begin(), kv.second.ids.end());
+    CK(cudaMalloc(&d_ids, sizeof(int32_t) * h_ids.size()));
+    CK(cudaMemcpyAsync(d_ids, h_ids.data(), sizeof(int32_t) * h_ids.size(), cudaMemcpyHostToDevice, stream));
     {
-        size_t off = 0;
+        std::lock_guard<std::mutex> lock(g_stream_mu);
+        const size_t nb = buckets.size();
+        while (g_side_streams.size() < nb) {
+            cudaStream_t s; cudaEvent_t e;
+            CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            g_side_streams.push_back(s); g_side_events.push_back(e);
+        }
+        if (!g_fork_event) CK(cudaEventCreateWithFlags(&g_fork_event, cudaEventDisableTiming));
+        CK(cudaEventRecord(g_fork_event, stream));
+        size_t off = 0; int bi = 0;
         for (auto &kv : buckets) {
-            const Config &cf = g_configs[kv.first / 4096];
-            const int threads = kv.first % 4096;
-            const size_t sm = bucket_smem[kv.first];
+            const Config &cf = g_configs[kv.first.first];
+            const int WLp = kv.first.second;
+            const int n_items = (int)kv.second.ids.size();
+            int threads, grid;
+            size_t sm;
+            const bool need_xax = !skip_aux || cf.grouped;
+            if (cf.grouped) { threads = (a.group_size * cf.L + 31) / 32 * 32; grid = n_items; sm = kv.second.smem; }
+            else {
+                // CTA size that keeps the most strings resident per SM (registers and shared memory both bound it)
+                const int regs = kernel_regs(cf);
+                int best = 32; long best_res = -1;
+                for (int th : {128, 96, 64, 32}) {
+                    if (th % cf.L) continue;
+                    const size_t b_ = smem_bytes_indep(cf, th / cf.L, a.Nx_t1, WLp, need_xax);
+                    if (b_ > 227 * 1024) continue;
+                    const long by_smem = (long)((227 * 1024) / (b_ + 1024)), by_regs = 65536 / ((long)regs * th);
+                    const long res = std::min(std::min(by_smem, by_regs), 32L) * th;
+                    if (res > best_res) { best_res = res; best = th; }
+                }
+                threads = best;
+                const int per = threads / cf.L; grid = (n_items + per - 1) / per;
+                sm = smem_bytes_indep(cf, threads / cf.L, a.Nx_t1, WLp, need_xax);
+            }
+            if (sm > 227 * 1024) {
+                snprintf(g_err, sizeof g_err, "a bucket (L=%d, ET=%d, %s) needs %zu bytes of shared memory (> 227 KB)", cf.L, cf.ET, cf.grouped ? "grouped" : "independent", sm);
+                rc = SFDTD_ERR_UNSUPPORTED; goto done;
+            }
             CK(cudaFuncSetAttribute(cf.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            K.group_ids = d_gids + off;
-            cf.kern<<<(unsigned)kv.second.size(), threads, sm, stream>>>(K);
+            K.ids = d_ids + off; K.n_items = n_items; K.WLp = WLp; K.need_xax = need_xax ? 1 : 0;
+            cudaStream_t s = (nb > 1) ? g_side_streams[bi] : stream;
+            if (nb > 1) CK(cudaStreamWaitEvent(s, g_fork_event, 0));
+            cf.kern<<<(unsigned)grid, threads, sm, s>>>(K);
             g_launches++;
             CK(cudaGetLastError());
-            off += kv.second.size();
+            if (nb > 1) { CK(cudaEventRecord(g_side_events[bi], s)); CK(cudaStreamWaitEvent(stream, g_side_events[bi], 0)); }
+            off += n_items; bi++;
         }
     }
     CK(cudaStreamSynchronize(stream));
 done:
+    if (rc != SFDTD_OK) cudaDeviceSynchronize();
     if (d_max) cudaFree(d_max);
-    if (d_gids) cudaFree(d_gids);
+    if (d_ids) cudaFree(d_ids);
+    if (d_wtab) cudaFree(d_wtab);
     return rc;
 }
