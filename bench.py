@@ -32,7 +32,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--strings", type=int, default=148 * GROUP, help="strings per GPU (multiple of 24)")
+    ap.add_argument("--strings", type=int, default=148 * GROUP * 4, help="strings per GPU (multiple of 24); BASELINE configs[4] sweeps 1k..1M")
     ap.add_argument("--length", type=float, default=1.0, help="seconds of audio per string")
     ap.add_argument("--excitation", default="pluck")
     ap.add_argument("--skip-aux", action="store_true")
@@ -184,9 +184,11 @@ def main():
     f64 = dict(dtype=torch.float64, device=dev)
     out = {n: torch.zeros(B, Nt, **f64) for n in ("uout", "zout", "v_r", "F_H", "u_H_out")}
 
+    uH = torch.empty_like(ctl["u_H"])
+
     def one_step(counters=False):
         su = p["state_u"].clone(); sz = p["state_z"].clone()
-        uH = ctl["u_H"].clone()
+        uH.copy_(ctl["u_H"])                      # u_H is updated in place by the stepper (string.cpp:303)
         return step_strings(
             su, sz, kappa=p["kappa"], alpha=p["alpha"], f0=ctl["f0"], pos=p["pos"], T60=p["T60"],
             x_b=ctl["x_b"], v_b=ctl["v_b"], F_b=ctl["F_b"], wid=ctl["wid"], phi_0=p["phi_0"], phi_1=p["phi_1"],
@@ -235,16 +237,20 @@ def main():
     # ---- end-to-end through the public API with host buffers (H2D of the compact parameters, D2H of the audio) ----
     e2e = None
     if not a.no_e2e:
+        del ctl, uH                              # the end-to-end path builds its own controls from the compact parameters
+        torch.cuda.empty_cache()
         pin = {kx: p_host[kx].pin_memory() for kx in sampler.TENSOR_KEYS}
         ph = dict(p_host); ph.update(pin)
-        h_u = torch.empty(B, Nt - 2, dtype=torch.float64).pin_memory()
-        h_z = torch.empty(B, Nt - 2, dtype=torch.float64).pin_memory()
+        rows = max(1, min(B, (256 << 20) // ((Nt - 2) * 8)))          # pinned staging buffer, <= 256 MiB
+        stage = torch.empty(rows, Nt - 2, dtype=torch.float64).pin_memory()
 
         def e2e_step():
             q = sampler.to_device(ph, dev, non_blocking=True)
-            r = sampler.run_compact(q, GROUP, skip_aux=a.skip_aux)
-            h_u.copy_(r["uout"][:, 2:], non_blocking=True)
-            h_z.copy_(r["zout"][:, 2:], non_blocking=True)
+            r = sampler.run_compact(q, GROUP, skip_aux=a.skip_aux, out=out)
+            for name in ("uout", "zout"):                              # device -> host read of the audio, all strings
+                for r0 in range(0, B, rows):
+                    r1 = min(B, r0 + rows)
+                    stage[: r1 - r0].copy_(r[name][r0:r1, 2:], non_blocking=True)
             torch.cuda.synchronize()
 
         e2e_step()

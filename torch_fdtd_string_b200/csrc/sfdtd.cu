@@ -35,6 +35,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 #include <map>
@@ -57,7 +58,7 @@ constexpr int NV = 28;              // doubles per time step in the per-string s
 constexpr int NI = 8;               // ints per time step
 constexpr int NOUT = 5;             // staged outputs per step
 constexpr int NCONST = 8;           // per-string constants kept in shared memory
-constexpr int GS_CAP = 200;         // cap on block Gauss-Seidel sweeps per solve
+constexpr int GS_CAP = 60;          // cap on block Gauss-Seidel sweeps per solve
 constexpr float GS_TOL = 1e-13f;    // predicted relative max-norm error that ends the sweeps
 constexpr int NLA_I = 6;            // longitudinal arrays per string, independent mode: Z1 Z2 ZA ZB RL P
 constexpr int NLA_G = 7;            // grouped mode: + ZP (previous fixed-point iterate)
@@ -129,10 +130,21 @@ __device__ __forceinline__ Derived derive(double f0, double kappa_rel, double al
 __device__ __forceinline__ int clampN(double v) { return (int)fmin(fmax(v, 0.0), 60000.0); }   // NaN -> 0
 
 // ---- prepass 1: per string, the largest N_t / N_l any step of this call can see (at min f0) ----------
-__global__ void sfdtd_prepass_kernel(const __grid_constant__ KArgs A, int32_t *maxNt, int32_t *maxNl) {
+// Also a per-string estimate of the nonlinearity  phi/h^2 Lambda^2  of the first step (from state row n-1): it predicts
+// how many block sweeps the string needs, and the host sorts the strings of a launch by it so that the strings
+// sharing a warp converge in about the same number of sweeps.
+__global__ void sfdtd_prepass_kernel(const __grid_constant__ KArgs A, int32_t *maxNt, int32_t *maxNl, float *est) {
     const int b = blockIdx.x;
     const int Nt = A.a.Nt;
     double fm = INFINITY;
+    double dm = 0.0;
+    {
+        const double *su1 = (const double *)A.a.state_u.ptr + (int64_t)b * A.a.state_u.bs + A.a.state_u.ts;
+        for (int i = 1 + threadIdx.x; i < A.a.Nx_t1; i += blockDim.x) dm = fmax(dm, fabs(su1[i] - su1[i - 1]));
+        for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(FULLMASK, dm, o));
+    }
+    __shared__ double sd[32];
+    if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = dm;
     if (A.a.f0.ts == 0) {
         fm = ldx(A.a.f0, b, 0);
     } else {
@@ -144,8 +156,13 @@ __global__ void sfdtd_prepass_kernel(const __grid_constant__ KArgs A, int32_t *m
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < (blockDim.x >> 5); w++) fm = fm < sm[w] ? fm : sm[w];
-        Derived d = derive(fm, lds(A.a.kappa, b), lds(A.a.alpha, b), A);
+        for (int w = 0; w < (blockDim.x >> 5); w++) dm = fmax(dm, sd[w]);
+        const double alpha = lds(A.a.alpha, b);
+        Derived d = derive(fm, lds(A.a.kappa, b), alpha, A);
         maxNt[b] = clampN(d.Nt); maxNl[b] = clampN(d.Nl);
+        const double phi = ((d.gamma * d.gamma) * A.k2) * (alpha * alpha - 1) / 4;
+        const double n2 = d.Nt * d.Nt;
+        est[b] = (float)(phi * n2 * n2 * dm * dm);
     }
 }
 
@@ -187,6 +204,14 @@ template <int L> __device__ __forceinline__ int red_or(int v) {
 }
 template <int L> constexpr int ilog2() { return L <= 1 ? 0 : 1 + ilog2<L / 2>(); }
 
+// |x| as the high word of the double: monotone in |x| for integer compares; NaN and inf sort above every finite value
+__device__ __forceinline__ unsigned hi_abs(double v) { return (unsigned)__double2hiint(v) & 0x7fffffffu; }
+__device__ __forceinline__ float hi_to_float(unsigned h) { return (float)__hiloint2double((int)h, 0); }   // > FLT_MAX -> inf, NaN -> NaN
+template <int L> __device__ __forceinline__ unsigned red_maxu(unsigned v) {
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULLMASK, v, o, L));
+    return v;
+}
 // fmaxf drops NaN operands: a NaN anywhere must still end the sweeps, so NaN is mapped to +inf here
 __device__ __forceinline__ float absf_nan_inf(double v) {
     const float f = fabsf((float)v);
@@ -663,6 +688,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 #pragma unroll
             for (int r = 0; r < ET; r++) xs[r] = 0.0;
             int zfo = z1o;
+            // All strings of a warp sweep until every one of them has converged (extra sweeps only tighten a
+            // converged string), so the loop body carries no per-string predication.
             auto gs_solve = [&](const double (&mr)[ET], bool need, bool first) {
                 bool conv = !need;
                 int sweeps = 0;
@@ -670,7 +697,6 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 int zco = first ? zao : zfo;
                 const int keep_l = tabi[jj * NI + I_KEEPL];
                 do {
-                    const bool act = !conv;
                     const int zno = (zco == zao) ? zbo : zao;
                     double d[ET];
                     {
@@ -692,72 +718,69 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         for (int r = 0; r < ET; r++) d[r] = (nuc[r + 1] - nuc[r]) - mr[r];
                     }
                     ts.solve(d, ln);
-                    float du = 0.f, su = 0.f;
+                    // max-norms of the change and of the solution, tracked on the high words of the doubles
+                    // (monotone in |x|, 2^-20 resolution; NaN/inf sort above every finite value)
+                    unsigned du = 0u, su = 0u;
 #pragma unroll
                     for (int r = 0; r < ET; r++) {
-                        du = fmaxf(du, absf_nan_inf(d[r] - xs[r]));
-                        if (sweeps == 0) su = fmaxf(su, absf_nan_inf(d[r]));
-                        if (act) xs[r] = d[r];
+                        du = max(du, hi_abs(d[r] - xs[r]));
+                        if (sweeps == 0) su = max(su, hi_abs(d[r]));
+                        xs[r] = d[r];
                     }
                     // q = mu (x_i - x_{i-1})  (the scale phi/h_t^2 and the 1/h_t of Dxb are folded into T_PHL)
                     double xl = shup<L>(xs[ET - 1], 1);
                     if (ln == 0) xl = 0.0;
-                    if (act) {
 #pragma unroll
-                        for (int r = 0; r < ET; r++) qs[i0row + r] = mu[r] * (xs[r] - (r == 0 ? xl : xs[r - 1]));
+                    for (int r = 0; r < ET; r++) qs[i0row + r] = mu[r] * (xs[r] - (r == 0 ? xl : xs[r - 1]));
+                    __syncwarp();
+                    for (int j = ln; j <= WLs; j += L) {
+                        const int li = LI[j];
+                        const double2 w = *(const double2 *)(LW + 2 * j);
+                        Lb[po + j] = w.x * qs[li & 0xffff] + w.y * qs[li >> 16];
                     }
                     __syncwarp();
-                    if (act) {
-                        for (int j = ln; j <= WLs; j += L) {
-                            const int li = LI[j];
-                            const double2 w = *(const double2 *)(LW + 2 * j);
-                            Lb[po + j] = w.x * qs[li & 0xffff] + w.y * qs[li >> 16];
-                        }
-                    }
-                    __syncwarp();
-                    float dz = 0.f, sz = 0.f;
-                    if (act) {
+                    unsigned dz = 0u, sz = 0u;
+                    {
                         const double PHL = t[T_PHL], idA = t[T_IDA], eidA = t[T_EIDA];
                         for (int j = ln; j < WLs; j += L) {
                             double rhs = PHL * (Lb[po + j + 1] - Lb[po + j]);
                             if (j < keep_l) rhs -= Lb[rlo + j];
                             const double zr = (j + 1 < WLs) ? Lb[zco + j + 1] : 0.0;
                             const double zn = rhs * idA - eidA * (Lb[zco + j - 1] + zr);
-                            dz = fmaxf(dz, absf_nan_inf(zn - Lb[zco + j]));
-                            sz = fmaxf(sz, absf_nan_inf(zn));
+                            dz = max(dz, hi_abs(zn - Lb[zco + j]));
+                            sz = max(sz, hi_abs(zn));
                             Lb[zno + j] = zn;
                         }
                     }
                     __syncwarp();
-                    if (act) zco = zno;
+                    zco = zno;
                     sweeps++;
                     bool ok;
                     if (sweeps == 1) {
-                        su = red_maxf<L>(su); sz = red_maxf<L>(sz);
-                        isu = 1.0f / su; isz = 1.0f / sz;          // 1/0 = inf: (0 * inf) = NaN is dropped by fmaxf below
-                        ok = false;
-                        if (!(su < INFINITY) || !(sz < INFINITY)) ok = true;      // NaN / inf state: nothing left to converge
+                        const float suf = hi_to_float(red_maxu<L>(su)), szf = hi_to_float(red_maxu<L>(sz));
+                        isu = __fdividef(1.0f, suf); isz = __fdividef(1.0f, szf);   // 1/0 = inf: (0 * inf) = NaN is dropped by fmaxf below
+                        ok = !(suf < INFINITY) || !(szf < INFINITY);                // NaN / inf state: nothing left to converge
                     } else {
                         // relative change of this sweep, both blocks; predicted error  e * rho / (1 - rho)
-                        float e = fmaxf(du * isu, dz * isz);
-                        e = red_maxf<L>(e);
+                        const unsigned dm = red_maxu<L>(max(du, 0u)), dzm = red_maxu<L>(dz);
+                        const float e = fmaxf(hi_to_float(dm) * isu, hi_to_float(dzm) * isz);
                         float rho = 2.0f * rho_h;
                         if (sweeps >= 3 && e_prev > 0.f) {
-                            const float rr = e / e_prev;
-                            if (act) rho_h = (rr > rho_h) ? rr : 0.5f * (rho_h + rr);
+                            const float rr = __fdividef(e, e_prev);
+                            if (!conv) rho_h = (rr > rho_h) ? rr : 0.5f * (rho_h + rr);
                             rho = 1.5f * rho_h;
                         }
                         rho = fminf(rho, 0.9f);
-                        const float est = e * rho / (1.0f - rho);
+                        const float est = e * __fdividef(rho, 1.0f - rho);
                         const int minS = (keep_l > 0) ? 4 : 2;
                         ok = (sweeps >= minS) && !(est > GS_TOL);
                         if (!(e < INFINITY)) ok = true;
                         e_prev = e;
-                        if (act && sweeps >= GS_CAP && !ok) { status |= SFDTD_ST_SOLVER_CAP; ok = true; }
+                        if (!conv && sweeps >= GS_CAP && !ok) { status |= SFDTD_ST_SOLVER_CAP; ok = true; }
                     }
-                    if (act) { cnt_sweeps += 1; conv = ok; }
+                    if (!conv) { cnt_sweeps += 1; conv = ok; }
                 } while (__any_sync(FULLMASK, !conv));
-                if (need) zfo = zco;
+                zfo = zco;
             };
 
             double vrel = 0.0, FH = 0.0, uH = 0.0;
@@ -1113,6 +1136,7 @@ struct Config { int L, ET, maxt; bool grouped; void (*kern)(const KArgs); };
 // grouped mode: one CTA per group, needs rows <= L*ET and ceil32(G*L) <= maxt.
 const Config g_configs[] = {
     CFG_I(8, 4, 3), CFG_I(8, 6, 2), CFG_I(16, 4, 3), CFG_I(16, 6, 2), CFG_I(32, 4, 3), CFG_I(32, 8, 1),
+    CFG_I(8, 4, 4), CFG_I(8, 6, 3), CFG_I(16, 4, 4), CFG_I(16, 6, 3), CFG_I(32, 4, 4), CFG_I(32, 8, 2),     // experimental: tighter register caps (SFDTD_TIGHT=1)
     CFG_G(8, 4, 256), CFG_G(8, 6, 256), CFG_G(16, 4, 512), CFG_G(16, 6, 384), CFG_G(32, 4, 1024), CFG_G(32, 8, 128), CFG_G(32, 8, 512),
 };
 constexpr int N_CONFIGS = sizeof(g_configs) / sizeof(g_configs[0]);
@@ -1200,12 +1224,15 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     int rc = SFDTD_OK;
     const int n_groups = (a.B + a.group_size - 1) / a.group_size;
     int32_t *d_max = nullptr, *d_ids = nullptr, *d_wtab = nullptr;
+    float *d_est = nullptr;
+    std::vector<float> h_est(a.B);
     std::vector<int32_t> h_max(2 * (size_t)a.B);
     std::vector<uint8_t> h_bow(a.B), h_ham(a.B);
     struct Bucket { std::vector<int32_t> ids; size_t smem = 0; };
     std::map<std::pair<int, int>, Bucket> buckets;      // (config index, WLp) -> items
     std::vector<int32_t> h_ids;
     const bool skip_aux = a.flags & SFDTD_SKIP_AUX;
+    const bool tight = getenv("SFDTD_TIGHT") && atoi(getenv("SFDTD_TIGHT")) != 0;
 
     KArgs K;
     memset(&K, 0, sizeof K);
@@ -1220,7 +1247,8 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
 
     CK(cudaMalloc(&d_max, sizeof(int32_t) * 2 * (size_t)a.B));
     CK(cudaMalloc(&d_wtab, sizeof(int32_t) * (size_t)n_groups * a.Nt));
-    sfdtd_prepass_kernel<<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B);
+    CK(cudaMalloc(&d_est, sizeof(float) * (size_t)a.B));
+    sfdtd_prepass_kernel<<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B, d_est);
     g_launches++;
     CK(cudaGetLastError());
     sfdtd_width_kernel<<<dim3((a.Nt + 127) / 128, n_groups), 128, 0, stream>>>(K, d_wtab);
@@ -1228,6 +1256,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     CK(cudaGetLastError());
     K.Wtab = d_wtab; K.maxNl = d_max + a.B;
     CK(cudaMemcpyAsync(h_max.data(), d_max, sizeof(int32_t) * 2 * (size_t)a.B, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h_est.data(), d_est, sizeof(float) * (size_t)a.B, cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(h_bow.data(), a.bow_mask, a.B, cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(h_ham.data(), a.hammer_mask, a.B, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
@@ -1245,7 +1274,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
             const int rows = std::min(Wt, h_max[g0 + s] + 3 + (h_bow[g0 + s] ? 8 : 0));
             if (!forced) {
                 int pick = -1;
-                for (int c = 0; c < N_CONFIGS && pick < 0; c++)
+                for (int c = tight ? 6 : 0; c < N_CONFIGS && pick < 0; c++)
                     if (!g_configs[c].grouped && rows <= g_configs[c].L * g_configs[c].ET) pick = c;
                 if (pick < 0) {
                     snprintf(g_err, sizeof g_err, "string %d: %d transverse rows are outside the built kernel set", g0 + s, rows);
@@ -1276,7 +1305,15 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
             bk.smem = std::max(bk.smem, dbl * sizeof(double) + 16);
         }
     }
-    for (auto &kv : buckets) h_ids.insert(h_ids.end(), kv.second.ids.begin(), kv.second.ids.end());
+    for (auto &kv : buckets) {
+        // independent mode: strings of similar nonlinearity share a warp (they converge in about the same number of sweeps)
+        if (!g_configs[kv.first.first].grouped)
+            std::stable_sort(kv.second.ids.begin(), kv.second.ids.end(), [&](int32_t x, int32_t y) {
+                const float ex = h_est[x], ey = h_est[y];
+                return (ex == ex ? ex : INFINITY) > (ey == ey ? ey : INFINITY);      // hardest first (they also run longest)
+            });
+        h_ids.insert(h_ids.end(), kv.second.ids.begin(), kv.second.ids.end());
+    }
     CK(cudaMalloc(&d_ids, sizeof(int32_t) * h_ids.size()));
     CK(cudaMemcpyAsync(d_ids, h_ids.data(), sizeof(int32_t) * h_ids.size(), cudaMemcpyHostToDevice, stream));
     {
@@ -1319,6 +1356,9 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
                 snprintf(g_err, sizeof g_err, "a bucket (L=%d, ET=%d, %s) needs %zu bytes of shared memory (> 227 KB)", cf.L, cf.ET, cf.grouped ? "grouped" : "independent", sm);
                 rc = SFDTD_ERR_UNSUPPORTED; goto done;
             }
+            if (getenv("SFDTD_VERBOSE"))
+                fprintf(stderr, "[sfdtd] bucket L=%d ET=%d %s WLp=%d items=%d threads=%d grid=%d smem=%zu regs=%d\n", cf.L, cf.ET,
+                        cf.grouped ? "grouped" : "indep", WLp, n_items, threads, grid, sm, kernel_regs(cf));
             CK(cudaFuncSetAttribute(cf.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             K.ids = d_ids + off; K.n_items = n_items; K.WLp = WLp; K.need_xax = need_xax ? 1 : 0;
             cudaStream_t s = (nb > 1) ? g_side_streams[bi] : stream;
@@ -1336,5 +1376,6 @@ done:
     if (d_max) cudaFree(d_max);
     if (d_ids) cudaFree(d_ids);
     if (d_wtab) cudaFree(d_wtab);
+    if (d_est) cudaFree(d_est);
     return rc;
 }

@@ -205,7 +205,7 @@ def compact_nbytes(p):
     return int(sum(p[kx].numel() * p[kx].element_size() for kx in TENSOR_KEYS))
 
 
-def run_compact(p_dev, group_size, surface_integral=True, skip_aux=False, counters=False, controls=None):
+def run_compact(p_dev, group_size, surface_integral=True, skip_aux=False, counters=False, controls=None, out=None):
     """compact device params -> audio: expands the controls on the device and runs the stepper."""
     from .forward_fn import step_strings
     dev = p_dev["kappa"].device
@@ -217,5 +217,6 @@ def run_compact(p_dev, group_size, surface_integral=True, skip_aux=False, counte
         x_H=p_dev["x_H"], w_H=p_dev["w_H"], M_r=p_dev["M_r"], alpha_H=p_dev["alpha_H"], u_H=c["u_H"].clone(),
         bow_mask=p_dev["bow_mask"], hammer_mask=p_dev["hammer_mask"], k=p_dev["k"], theta_t=p_dev["theta_t"],
         lambda_c=p_dev["lambda_c"], relative_order=p_dev["relative_order"], Nt=p_dev["Nt"], group_size=group_size,
-        surface_integral=surface_integral, save_state=False, skip_aux=skip_aux, p_a=p_dev["p_a"], counters=counters)
+        surface_integral=surface_integral, save_state=False, skip_aux=skip_aux, p_a=p_dev["p_a"], counters=counters, out=out,
+        check=False)
     return res
