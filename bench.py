@@ -21,6 +21,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the stepper launches one kernel per string-size bucket on its own stream: give every stream its own hardware queue
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 SR = 48000
 GROUP = 24                      # task.batch_size of experiment=nsynth-like
@@ -217,11 +219,14 @@ def main():
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    marks = []
     for _ in range(a.steps):
         one_step()
+        ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append(ev)
     e1.record()
     barrier()
     t_dev = e0.elapsed_time(e1) * 1e-3
+    step_ms = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(len(marks))]
     launches = launch_count() - l0
     clk = clocks.stop()
     tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
@@ -314,7 +319,7 @@ def main():
         "grid_point_updates_per_s": world * gpu_upd / per_step,
         "mean_operator_widths": {"W_t": Wt_mean, "W_l": Wl_mean},
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": int(launches), "clocks": clk,
+        "gpu_launches": int(launches), "clocks": clk, "step_ms": [round(x, 2) for x in step_ms],
         "health": {"status_bits": status, "nan_strings": nan_strings,
                    "mean_outer_iters": float(counters[:, 0].sum()) / max(1.0, float(counters[:, 3].sum())),
                    "mean_sweeps_per_step": float(counters[:, 1].sum()) / max(1.0, float(counters[:, 3].sum())),

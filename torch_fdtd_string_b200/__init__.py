@@ -5,6 +5,12 @@ Public surface (mirrors the reference for this path only):
   process(...)               -- reference src/task/simulate.py:16-119 (the chunk driver)
   step_strings(...)          -- native compact-input API (no (B,Nt,Nx) tensors)
 """
+import os as _os
+
+# The stepper launches one kernel per string-size bucket, each on its own stream; with the default of 8 hardware
+# queues those streams alias and serialise.  Only effective when set before the CUDA context is created.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from .forward_fn import forward_fn, step_strings, make_xax, launch_count  # noqa: F401
 from .simulate import process  # noqa: F401
 

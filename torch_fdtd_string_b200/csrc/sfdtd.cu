@@ -54,7 +54,8 @@
 namespace {
 
 constexpr int WL_MARGIN = 2;        // ghost rows of the longitudinal block kept beyond N_l (decay (e/d)^m, e/d ~ 1e-5)
-constexpr int NV = 28;              // doubles per time step in the per-string scalar table
+constexpr int NV_I = 22;            // doubles per time step in the per-string scalar table, independent mode
+constexpr int NV_G = 26;            // grouped mode: + tolerances, bow force
 constexpr int NI = 8;               // ints per time step
 constexpr int NOUT = 5;             // staged outputs per step
 constexpr int NCONST = 8;           // per-string constants kept in shared memory
@@ -66,8 +67,9 @@ constexpr int TBS = 8;              // time steps per scalar-table block
 
 // table slots (doubles)
 enum { T_IHT = 0, T_OFFA, T_DIAGA, T_CORR, T_OFFC, T_DIAGC, T_DIAGB, T_OFF1B, T_KH4, T_PH2, T_PHL, T_IDA, T_EIDA,
-       T_RDW, T_TOLT, T_TOLL, T_CTR, T_VB, T_FB, T_WID, T_UHPRE, T_HT, T_IHL, T_S0K, T_S1K, T_G, T_GA2, T_PHI };
-static_assert(T_PHI < NV, "table too small");
+       T_RDW, T_CTR, T_VB, T_WID, T_UHPRE, T_IHL, T_S0K, T_S1K, T_GA2,      // <- independent mode uses the slots up to here
+       T_TOLT, T_TOLL, T_FB, T_SPARE };
+static_assert(T_GA2 < NV_I && T_SPARE < NV_G, "table too small");
 // table slots (ints)
 enum { I_NT = 0, I_NL, I_R, I_WLS, I_RK, I_KEEPL, I_IDXH, I_IC };
 // per-string constants
@@ -326,7 +328,7 @@ template <int L, int ET> __device__ __forceinline__ double fetch_row(const doubl
 // shared-memory doubles of the fixed part of a string slot, and of its longitudinal part (W rows incl. guards, W even)
 __host__ __device__ inline int slot_fixed_doubles(int L, int ET, bool grouped) {
     const int LE = L * ET;
-    int n = TBS * NV + TBS * NI / 2 + TBS * NOUT + NCONST + (LE + 2) + 2 * (LE + 4) + (grouped ? LE : 0);
+    int n = TBS * (grouped ? NV_G : NV_I) + TBS * NI / 2 + TBS * NOUT + NCONST + (LE + 2) + 2 * (LE + 4) + (grouped ? LE : 0);
     n = (n + 1) & ~1;                 // 16-byte aligned slots (int4 / double2 loads)
     if ((n & 15) == 0) n += 2;        // ... that do not start in the same bank
     return n;
@@ -340,6 +342,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
     constexpr int TB = TBS;
     constexpr int LE = L * ET;
     constexpr int NLA = GROUPED ? NLA_G : NLA_I;
+    constexpr int NV = GROUPED ? NV_G : NV_I;
     // fixed slot layout (offsets in doubles)
     constexpr int O_TABI = TB * NV, O_OST = O_TABI + TB * NI / 2, O_CST = O_OST + TB * NOUT, O_QS = O_CST + NCONST;
     constexpr int O_UA = O_QS + LE + 2 + 2, O_UB = O_UA + LE + 4, O_RC = O_UB + LE + 2;
@@ -525,18 +528,18 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 int WLs = min(N_l + 1 + WL_MARGIN, Wl);
                 if (WLs > WLa) { WLs = WLa; oob = 1; }
                 const int keep_flat = N_t + N_l + 2;                         // string.cpp:233
-                t[T_IHT] = iht; t[T_IHL] = ihl; t[T_HT] = d.ht;
+                t[T_IHT] = iht; t[T_IHL] = ihl;
                 t[T_OFFA] = offA; t[T_DIAGA] = diagA; t[T_CORR] = corr;
                 t[T_OFFC] = 0.5 * A.omth + s1k * iht2; t[T_DIAGC] = A.th - s0k - 2 * s1k * iht2;
                 t[T_DIAGB] = -2 * A.th + 2 * g * iht2 + 6 * kh4; t[T_OFF1B] = -A.omth - g * iht2 - 4 * kh4; t[T_KH4] = kh4;
-                t[T_PH2] = phi * iht2; t[T_PHL] = (phi != 0.0) ? ihl * d.ht : 0.0; t[T_PHI] = phi;
+                t[T_PH2] = phi * iht2; t[T_PHL] = (phi != 0.0) ? ihl * d.ht : 0.0;
                 t[T_IDA] = idA; t[T_EIDA] = eA * idA;
                 t[T_RDW] = ((0.5 * d.ht) * exc) * A.ik;                      // surface-integral weight / k (string.cpp:274-291)
-                t[T_TOLT] = pow(d.ht, A.order); t[T_TOLL] = pow(d.hl, A.order);
+                if (GROUPED) { t[T_TOLT] = pow(d.ht, A.order); t[T_TOLL] = pow(d.hl, A.order); t[T_FB] = ldx(a.F_b, b, n); }
                 t[T_CTR] = ctr; t[T_WID] = wid;
-                t[T_VB] = ldx(a.v_b, b, n); t[T_FB] = ldx(a.F_b, b, n);
+                t[T_VB] = ldx(a.v_b, b, n);
                 t[T_UHPRE] = ldx(a.u_H, b, n);
-                t[T_S0K] = s0k; t[T_S1K] = s1k; t[T_G] = g; t[T_GA2] = g * alpha2;
+                t[T_S0K] = s0k; t[T_S1K] = s1k; t[T_GA2] = g * alpha2;
                 ti[I_NT] = N_t; ti[I_NL] = N_l; ti[I_R] = R | (oob << 30); ti[I_WLS] = WLs;
                 ti[I_RK] = min(R, keep_flat); ti[I_KEEPL] = keep_flat - NXT;
                 ti[I_IDXH] = (int)fmin(fmax(floor(__dmul_rn(xH, (double)(N_t - 1))), 0.0), (double)(LE - 1));
@@ -876,7 +879,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     const double ex = cst[C_AHM1];
                     r1pow = (ex == 2.0) ? r1 * r1 : ((ex == 0.0) ? 1.0 : pow(r1, ex));
                 }
-                const double tol_t = t[T_TOLT], tol_l = t[T_TOLL];
+                const double tol_t = GROUPED ? t[T_TOLT] : 0.0, tol_l = GROUPED ? t[T_TOLL] : 0.0;
                 // the iterate starts as the unmasked state[n-1] (string.cpp:190-191)
 #pragma unroll
                 for (int r = 0; r < ET; r++) nu[r] = S[u1o + i0row + r];
@@ -930,7 +933,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     const bool need = !solved || forced;
                     if (__any_sync(FULLMASK, need)) {
                         double mr[ET];
-                        const double sB = -k2 * (t[T_FB] * hb) * t[T_IHT];
+                        const double sB = -k2 * ((GROUPED ? t[T_FB] : 0.0) * hb) * t[T_IHT];
                         const double sH = hamm ? nan0(-k2 * (cst[C_MR] * FH)) : 0.0;
 #pragma unroll
                         for (int r = 0; r < ET; r++) {
@@ -1129,16 +1132,19 @@ __global__ void __launch_bounds__(256) sfdtd_fma_peak_kernel(T *out, int iters, 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 
-struct Config { int L, ET, maxt; bool grouped; void (*kern)(const KArgs); };
-#define CFG_I(L_, ET_, MB_) Config{L_, ET_, 128, false, sfdtd_step_kernel<L_, ET_, false, 128, MB_>}
-#define CFG_G(L_, ET_, MT_) Config{L_, ET_, MT_, true, sfdtd_step_kernel<L_, ET_, true, MT_, 1>}
-// smallest first.  independent mode: 128-thread CTAs, a string needs rows <= L*ET.
+struct Config { int L, ET, maxt; bool grouped; int tier; void (*kern)(const KArgs); };
+#define CFG_I(L_, ET_, MB_, TIER_) Config{L_, ET_, 128, false, TIER_, sfdtd_step_kernel<L_, ET_, false, 128, MB_>}
+#define CFG_G(L_, ET_, MT_) Config{L_, ET_, MT_, true, 0, sfdtd_step_kernel<L_, ET_, true, MT_, 1>}
+// smallest first.  independent mode: <=128-thread CTAs, a string needs rows <= L*ET; tier = register budget variant
+// (0: up to 255/168 registers, 1: 168 everywhere, 2: 128 for the 4-row kernels; SFDTD_TIER selects, default below).
 // grouped mode: one CTA per group, needs rows <= L*ET and ceil32(G*L) <= maxt.
 const Config g_configs[] = {
-    CFG_I(8, 4, 3), CFG_I(8, 6, 2), CFG_I(16, 4, 3), CFG_I(16, 6, 2), CFG_I(32, 4, 3), CFG_I(32, 8, 1),
-    CFG_I(8, 4, 4), CFG_I(8, 6, 3), CFG_I(16, 4, 4), CFG_I(16, 6, 3), CFG_I(32, 4, 4), CFG_I(32, 8, 2),     // experimental: tighter register caps (SFDTD_TIGHT=1)
+    CFG_I(8, 4, 3, 0), CFG_I(8, 6, 2, 0), CFG_I(16, 4, 3, 0), CFG_I(16, 6, 2, 0), CFG_I(32, 4, 3, 0), CFG_I(32, 8, 1, 0),
+    CFG_I(8, 4, 3, 1), CFG_I(8, 6, 3, 1), CFG_I(16, 4, 3, 1), CFG_I(16, 6, 3, 1), CFG_I(32, 4, 3, 1), CFG_I(32, 8, 2, 1),
+    CFG_I(8, 4, 4, 2), CFG_I(8, 6, 3, 2), CFG_I(16, 4, 4, 2), CFG_I(16, 6, 3, 2), CFG_I(32, 4, 4, 2), CFG_I(32, 8, 2, 2),
     CFG_G(8, 4, 256), CFG_G(8, 6, 256), CFG_G(16, 4, 512), CFG_G(16, 6, 384), CFG_G(32, 4, 1024), CFG_G(32, 8, 128), CFG_G(32, 8, 512),
 };
+constexpr int DEFAULT_TIER = 0;
 constexpr int N_CONFIGS = sizeof(g_configs) / sizeof(g_configs[0]);
 
 // longitudinal allocation classes of the independent mode (rows incl. the two guards)
@@ -1160,6 +1166,22 @@ int kernel_regs(const Config &c) {
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, c.kern) != cudaSuccess) { cudaGetLastError(); return 255; }
     return fa.numRegs;
+}
+
+// grow-only device scratch (per device), so that a call does not pay cudaMalloc / cudaFree (both synchronise the device)
+struct Scratch { void *p = nullptr; size_t cap = 0; };
+std::map<std::pair<int, int>, Scratch> g_scratch;      // (device, slot) -> buffer
+cudaError_t scratch_get(int dev, int slot, size_t bytes, void **out) {
+    Scratch &sc = g_scratch[{dev, slot}];
+    if (sc.cap < bytes) {
+        if (sc.p) { cudaError_t e = cudaFree(sc.p); if (e != cudaSuccess) return e; sc.p = nullptr; sc.cap = 0; }
+        const size_t cap = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&sc.p, cap);
+        if (e != cudaSuccess) return e;
+        sc.cap = cap;
+    }
+    *out = sc.p;
+    return cudaSuccess;
 }
 
 // side streams so that the launches of different buckets overlap
@@ -1221,18 +1243,20 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     if (a.Nt <= 2) return SFDTD_OK;
 
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    int rc = SFDTD_OK;
+    int rc = SFDTD_OK, dev = 0;
+    bool locked = false;
     const int n_groups = (a.B + a.group_size - 1) / a.group_size;
     int32_t *d_max = nullptr, *d_ids = nullptr, *d_wtab = nullptr;
     float *d_est = nullptr;
     std::vector<float> h_est(a.B);
     std::vector<int32_t> h_max(2 * (size_t)a.B);
     std::vector<uint8_t> h_bow(a.B), h_ham(a.B);
-    struct Bucket { std::vector<int32_t> ids; size_t smem = 0; };
+    struct Bucket { std::vector<int32_t> ids; size_t smem = 0, off = 0; };
     std::map<std::pair<int, int>, Bucket> buckets;      // (config index, WLp) -> items
     std::vector<int32_t> h_ids;
+    size_t n_ids_total = 0;
     const bool skip_aux = a.flags & SFDTD_SKIP_AUX;
-    const bool tight = getenv("SFDTD_TIGHT") && atoi(getenv("SFDTD_TIGHT")) != 0;
+    const int tier = getenv("SFDTD_TIER") ? std::min(2, std::max(0, atoi(getenv("SFDTD_TIER")))) : DEFAULT_TIER;
 
     KArgs K;
     memset(&K, 0, sizeof K);
@@ -1245,9 +1269,11 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     K.mhd = (double)(-0.01f);                                                // hammer.cpp:3
     K.max_iter = a.max_iter > 0 ? a.max_iter : 1000;
 
-    CK(cudaMalloc(&d_max, sizeof(int32_t) * 2 * (size_t)a.B));
-    CK(cudaMalloc(&d_wtab, sizeof(int32_t) * (size_t)n_groups * a.Nt));
-    CK(cudaMalloc(&d_est, sizeof(float) * (size_t)a.B));
+    CK(cudaGetDevice(&dev));
+    g_stream_mu.lock(); locked = true;          // scratch buffers and side streams are shared by all callers
+    CK(scratch_get(dev, 0, sizeof(int32_t) * 2 * (size_t)a.B, (void **)&d_max));
+    CK(scratch_get(dev, 1, sizeof(int32_t) * (size_t)n_groups * a.Nt, (void **)&d_wtab));
+    CK(scratch_get(dev, 2, sizeof(float) * (size_t)a.B, (void **)&d_est));
     sfdtd_prepass_kernel<<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B, d_est);
     g_launches++;
     CK(cudaGetLastError());
@@ -1273,9 +1299,13 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
             // rows a string can need: its own N_t + 3 (+ the bow window of a bowed string), never more than W_t
             const int rows = std::min(Wt, h_max[g0 + s] + 3 + (h_bow[g0 + s] ? 8 : 0));
             if (!forced) {
+                // lanes: enough rows for the transverse block, and enough lanes that the longitudinal loops stay short
+                const int wlc = wl_class(long_rows(h_max[a.B + g0 + s]));
+                const int min_lanes = std::min(32, wlc / 4);
                 int pick = -1;
-                for (int c = tight ? 6 : 0; c < N_CONFIGS && pick < 0; c++)
-                    if (!g_configs[c].grouped && rows <= g_configs[c].L * g_configs[c].ET) pick = c;
+                for (int c = 0; c < N_CONFIGS && pick < 0; c++)
+                    if (!g_configs[c].grouped && g_configs[c].tier == tier && rows <= g_configs[c].L * g_configs[c].ET &&
+                        g_configs[c].L >= min_lanes) pick = c;
                 if (pick < 0) {
                     snprintf(g_err, sizeof g_err, "string %d: %d transverse rows are outside the built kernel set", g0 + s, rows);
                     rc = SFDTD_ERR_UNSUPPORTED; goto done;
@@ -1306,6 +1336,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
         }
     }
     for (auto &kv : buckets) {
+        kv.second.off = n_ids_total; n_ids_total += kv.second.ids.size();
         // independent mode: strings of similar nonlinearity share a warp (they converge in about the same number of sweeps)
         if (!g_configs[kv.first.first].grouped)
             std::stable_sort(kv.second.ids.begin(), kv.second.ids.end(), [&](int32_t x, int32_t y) {
@@ -1314,10 +1345,9 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
             });
         h_ids.insert(h_ids.end(), kv.second.ids.begin(), kv.second.ids.end());
     }
-    CK(cudaMalloc(&d_ids, sizeof(int32_t) * h_ids.size()));
+    CK(scratch_get(dev, 3, sizeof(int32_t) * h_ids.size(), (void **)&d_ids));
     CK(cudaMemcpyAsync(d_ids, h_ids.data(), sizeof(int32_t) * h_ids.size(), cudaMemcpyHostToDevice, stream));
     {
-        std::lock_guard<std::mutex> lock(g_stream_mu);
         const size_t nb = buckets.size();
         while (g_side_streams.size() < nb) {
             cudaStream_t s; cudaEvent_t e;
@@ -1327,11 +1357,22 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
         }
         if (!g_fork_event) CK(cudaEventCreateWithFlags(&g_fork_event, cudaEventDisableTiming));
         CK(cudaEventRecord(g_fork_event, stream));
-        size_t off = 0; int bi = 0;
-        for (auto &kv : buckets) {
+        // launch order: largest buckets first
+        typedef std::pair<const std::pair<int, int>, Bucket> BK;
+        std::vector<BK *> order;
+        for (auto &kv : buckets) order.push_back(&kv);
+        std::stable_sort(order.begin(), order.end(), [&](const BK *x, const BK *y) {
+            const Config &cx = g_configs[x->first.first], &cy = g_configs[y->first.first];
+            (void)cx; (void)cy;
+            return x->second.ids.size() > y->second.ids.size();
+        });
+        int bi = 0;
+        for (BK *pkv : order) {
+            BK &kv = *pkv;
             const Config &cf = g_configs[kv.first.first];
             const int WLp = kv.first.second;
             const int n_items = (int)kv.second.ids.size();
+            const size_t off = kv.second.off;
             int threads, grid;
             size_t sm;
             const bool need_xax = !skip_aux || cf.grouped;
@@ -1345,7 +1386,8 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
                     const size_t b_ = smem_bytes_indep(cf, th / cf.L, a.Nx_t1, WLp, need_xax);
                     if (b_ > 227 * 1024) continue;
                     const long by_smem = (long)((227 * 1024) / (b_ + 1024)), by_regs = 65536 / ((long)regs * th);
-                    const long res = std::min(std::min(by_smem, by_regs), 32L) * th;
+                    long res = std::min(std::min(by_smem, by_regs), 32L) * th;
+                    if (b_ > 76 * 1024 && th > 32) res /= 2;      // large CTAs cannot share an SM with other buckets: prefer smaller ones
                     if (res > best_res) { best_res = res; best = th; }
                 }
                 threads = best;
@@ -1360,6 +1402,8 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
                 fprintf(stderr, "[sfdtd] bucket L=%d ET=%d %s WLp=%d items=%d threads=%d grid=%d smem=%zu regs=%d\n", cf.L, cf.ET,
                         cf.grouped ? "grouped" : "indep", WLp, n_items, threads, grid, sm, kernel_regs(cf));
             CK(cudaFuncSetAttribute(cf.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            // one shared-memory carve-out for every bucket kernel, so that CTAs of different buckets can share an SM
+            CK(cudaFuncSetAttribute(cf.kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             K.ids = d_ids + off; K.n_items = n_items; K.WLp = WLp; K.need_xax = need_xax ? 1 : 0;
             cudaStream_t s = (nb > 1) ? g_side_streams[bi] : stream;
             if (nb > 1) CK(cudaStreamWaitEvent(s, g_fork_event, 0));
@@ -1367,15 +1411,12 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
             g_launches++;
             CK(cudaGetLastError());
             if (nb > 1) { CK(cudaEventRecord(g_side_events[bi], s)); CK(cudaStreamWaitEvent(stream, g_side_events[bi], 0)); }
-            off += n_items; bi++;
+            bi++;
         }
     }
     CK(cudaStreamSynchronize(stream));
 done:
     if (rc != SFDTD_OK) cudaDeviceSynchronize();
-    if (d_max) cudaFree(d_max);
-    if (d_ids) cudaFree(d_ids);
-    if (d_wtab) cudaFree(d_wtab);
-    if (d_est) cudaFree(d_est);
+    if (locked) g_stream_mu.unlock();
     return rc;
 }
