@@ -164,11 +164,13 @@ def f0_min_over_time(p, Nt, k, block=4096):
     return lo
 
 
-def expand_controls(p, device):
-    """compact description (already on `device`) -> dict of (B,Nt) float64 control curves on the device."""
+def expand_controls(p, device, n_run=None):
+    """compact description (already on `device`) -> dict of (B,n_run) float64 control curves on the device:
+    the first `n_run` samples (default: all `Nt`) of the curves defined over the full length `Nt`."""
     Nt, k, sr = p["Nt"], p["k"], p["sr"]
     B = p["B"]
-    t = torch.arange(1, Nt + 1, dtype=torch.float64, device=device).view(1, -1)
+    n_run = Nt if n_run is None else int(n_run)
+    t = torch.arange(1, n_run + 1, dtype=torch.float64, device=device).view(1, -1)
     ramp = (t - 1) / max(Nt - 1, 1)
     lin = lambda a, b: a.view(-1, 1) + (b - a).view(-1, 1) * ramp
     f0 = _f0_curve(p, Nt, k, t)
@@ -179,8 +181,8 @@ def expand_controls(p, device):
     off = (Nt - (sr * p["pulloff"]).floor()).view(-1, 1)
     w = torch.tanh((Nt - (t - 1) - off).clamp(min=0) / sr * 100)
     F_b = torch.where(p["pulloff"].view(-1, 1) > 0, F_b * w, F_b)
-    wid = p["wid"].view(-1, 1).expand(B, Nt)                                          # time stride 0
-    u_H = torch.zeros(B, Nt, dtype=torch.float64, device=device)                      # simulator.py:573-578
+    wid = p["wid"].view(-1, 1).expand(B, n_run)                                       # time stride 0
+    u_H = torch.zeros(B, n_run, dtype=torch.float64, device=device)                      # simulator.py:573-578
     u_H[:, :2] = -1e-3
     u_H[:, 1] += k * p["v_H"]
     return dict(f0=f0, x_b=x_b, v_b=v_b, F_b=F_b, wid=wid, u_H=u_H)
@@ -205,18 +207,21 @@ def compact_nbytes(p):
     return int(sum(p[kx].numel() * p[kx].element_size() for kx in TENSOR_KEYS))
 
 
-def run_compact(p_dev, group_size, surface_integral=True, skip_aux=False, counters=False, controls=None, out=None):
-    """compact device params -> audio: expands the controls on the device and runs the stepper."""
+def run_compact(p_dev, group_size, surface_integral=True, skip_aux=False, counters=False, controls=None, out=None,
+                n_run=None):
+    """compact device params -> audio: expands the controls on the device and runs the stepper for the first
+    `n_run` samples (default: the full length)."""
     from .forward_fn import step_strings
     dev = p_dev["kappa"].device
-    c = controls if controls is not None else expand_controls(p_dev, dev)
+    n_run = p_dev["Nt"] if n_run is None else int(n_run)
+    c = controls if controls is not None else expand_controls(p_dev, dev, n_run)
     su = p_dev["state_u"].clone(); sz = p_dev["state_z"].clone()
     res = step_strings(
         su, sz, kappa=p_dev["kappa"], alpha=p_dev["alpha"], f0=c["f0"], pos=p_dev["pos"], T60=p_dev["T60"],
         x_b=c["x_b"], v_b=c["v_b"], F_b=c["F_b"], wid=c["wid"], phi_0=p_dev["phi_0"], phi_1=p_dev["phi_1"],
         x_H=p_dev["x_H"], w_H=p_dev["w_H"], M_r=p_dev["M_r"], alpha_H=p_dev["alpha_H"], u_H=c["u_H"].clone(),
         bow_mask=p_dev["bow_mask"], hammer_mask=p_dev["hammer_mask"], k=p_dev["k"], theta_t=p_dev["theta_t"],
-        lambda_c=p_dev["lambda_c"], relative_order=p_dev["relative_order"], Nt=p_dev["Nt"], group_size=group_size,
+        lambda_c=p_dev["lambda_c"], relative_order=p_dev["relative_order"], Nt=n_run, group_size=group_size,
         surface_integral=surface_integral, save_state=False, skip_aux=skip_aux, p_a=p_dev["p_a"], counters=counters, out=out,
         check=False)
     return res
