@@ -594,7 +594,28 @@ int sfdtd_oracle_forward(sfdtd_oracle_args *a)
                     const double dA = w->A[(size_t)(Wt) * nw + Wt], eA = (Wl > 1) ? w->A[(size_t)(Wt) * nw + Wt + 1] : 0.0;
                     for (int j = 0; j < Wl; j++) { zc[j] = w->z1[j]; zn[j] = 0.0; }
                     for (int i = 0; i < Wt; i++) uu[i] = 0.0;
-                    for (int j = 0; j < Wl; j++) kl[j] = 2 * w->z1[j] - w->z2[j];
+                    {
+                        const int g2 = getenv("SFDTD_GUESS2") ? atoi(getenv("SFDTD_GUESS2")) : 2;
+                        const double *sz3 = (n >= 3) ? a->state_z + ((size_t)b * Nt + (n - 3)) * NXL : NULL;
+                        for (int j = 0; j < Wl; j++) {
+                            if (g2 == 4) kl[j] = 0.0;
+                            else if (g2 == 3 && sz3) kl[j] = 3 * w->z1[j] - 3 * w->z2[j] + ((j <= N_l) ? sz3[j] : 0.0);
+                            else if (g2 == 1) kl[j] = w->z1[j];
+                            else kl[j] = 2 * w->z1[j] - w->z2[j];
+                        }
+                    }
+                    if (getenv("SFDTD_GUESS2") && atoi(getenv("SFDTD_GUESS2")) == 4) {
+                        /* slaved guess: z0 = A22^-1 (-r_l - K_lt (2 u1 - u2)) (one Jacobi application around z1) */
+                        for (int i = 0; i < Wt; i++) uu[i] = (i < R) ? 2 * w->u1[i] - w->u2[i] : 0.0;
+                        if (phi_ != 0.0) apply_Klt(w, Wt, Wl, phi_, uu, kz, sc1); else for (int j = 0; j < Wl; j++) kz[j] = 0.0;
+                        for (int j = 0; j < WLs; j++) {
+                            const double zl = j > 0 ? w->z1[j - 1] : 0.0, zr = (j + 1 < WLs) ? w->z1[j + 1] : 0.0;
+                            kl[j] = ((-w->rhs[Wt + j] - kz[j]) - eA * (zl + zr)) / dA;
+                        }
+                        for (int j = WLs; j < Wl; j++) kl[j] = 0.0;
+                        for (int j = 0; j < Wl; j++) zc[j] = kl[j];
+                        for (int i = 0; i < Wt; i++) uu[i] = 0.0;
+                    }
                     int sweeps = 0; double du_prev = 0, su_ = 0;
                     const double TOL = getenv("SFDTD_TOL2") ? atof(getenv("SFDTD_TOL2")) : 1e-13;
                     static __thread double rho_hist[4096];
@@ -628,6 +649,8 @@ int sfdtd_oracle_forward(sfdtd_oracle_args *a)
                         double dz = 0, sz_ = 0;
                         for (int j = 0; j < WLs; j++) { double e = fabs(zc[j] - zn[j]); if (e > dz) dz = e; e = fabs(zc[j]); if (e > sz_) sz_ = e; }
                         const double estz = dz * rho / (1 - rho);
+                        if (getenv("SFDTD_TRACE") && n == atoi(getenv("SFDTD_TRACE")) && b < 6)
+                            fprintf(stderr, "n=%d b=%d sweep=%d du/su=%.2e dz/sz=%.2e rho=%.3f est=%.2e estz=%.2e\n", n, b, sweeps, du / su_, dz / sz_, rho, est / su_, estz / sz_);
                         if (sweeps >= minS && !(est > TOL * su_) && !(estz > TOL * sz_)) break;      /* also exits on NaN */
                         if (sweeps >= 500) { status = 2; break; }
                     }

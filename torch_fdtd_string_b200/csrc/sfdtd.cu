@@ -42,6 +42,7 @@
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <chrono>
 
 #include "sfdtd.h"
 
@@ -60,7 +61,8 @@ constexpr int NI = 8;               // ints per time step
 constexpr int NOUT = 5;             // staged outputs per step
 constexpr int NCONST = 8;           // per-string constants kept in shared memory
 constexpr int GS_CAP = 60;          // cap on block Gauss-Seidel sweeps per solve
-constexpr float GS_TOL = 1e-13f;    // predicted relative max-norm error that ends the sweeps
+constexpr float GS_TOL = 1e-13f;    // predicted relative max-norm error of the transverse block that ends the sweeps
+constexpr float GS_TOL_Z = 1e-11f;  // ... of the longitudinal block (its relative change lags the transverse one by 20-50x)
 constexpr int NLA_I = 6;            // longitudinal arrays per string, independent mode: Z1 Z2 ZA ZB RL P
 constexpr int NLA_G = 7;            // grouped mode: + ZP (previous fixed-point iterate)
 constexpr int TBS = 8;              // time steps per scalar-table block
@@ -766,7 +768,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     } else {
                         // relative change of this sweep, both blocks; predicted error  e * rho / (1 - rho)
                         const unsigned dm = red_maxu<L>(max(du, 0u)), dzm = red_maxu<L>(dz);
-                        const float e = fmaxf(hi_to_float(dm) * isu, hi_to_float(dzm) * isz);
+                        const float e = fmaxf(hi_to_float(dm) * isu, hi_to_float(dzm) * (isz * (GS_TOL / GS_TOL_Z)));
                         float rho = 2.0f * rho_h;
                         if (sweeps >= 3 && e_prev > 0.f) {
                             const float rr = __fdividef(e, e_prev);
@@ -787,6 +789,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
             };
 
             double vrel = 0.0, FH = 0.0, uH = 0.0;
+            double bnum = 0.0, bden = 0.0;
             double nu[ET];
 
             // ---- bow: raised-cosine weights over the Nx_t1-point axis (bow.cpp:32, misc.cpp:20-34) ----
@@ -818,6 +821,25 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 
             if (!GROUPED) {
                 // ================= independent mode: unforced string, one solve =================
+                // v_r of an un-bowed string (the reference evaluates it for every string, bow.cpp:35-38): the raised-cosine
+                // window weights are computed before the solve, branch-free, so that their latency overlaps with it
+                double bw0 = 0.0, bw1 = 0.0;
+                if (do_bow) {
+                    const double ctr = t[T_CTR], wid = t[T_WID];
+                    const double hw = wid * 0.5, iw2 = 2.0 * frcp(wid);
+                    bow_ic = tabi[jj * NI + I_IC];
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const int i = bow_ic + c * L + ln;
+                        const double x = (double)xaxs[min(i, NXT - 1)];
+                        const double dm = __dsub_rn(__dsub_rn(x, ctr), hw), dp = __dadd_rn(__dsub_rn(x, ctr), hw);
+                        const double p = __dmul_rn(-dm, dp);
+                        double o = 0.5 * (1.0 + cospi((x - ctr) * iw2));
+                        o = (p > 0 && i < NXT) ? o : ((p != p && i < NXT) ? p : 0.0);
+                        if (((c == 1 && ln == L - 1) || i >= LE) && o != 0.0) status |= SFDTD_ST_BOW_WINDOW;
+                        if (c == 0) bw0 = o; else bw1 = o;
+                    }
+                }
                 gs_solve(rt, true, true);
                 cnt_outer += 2;      // the reference's second pass reproduces the first (residual 0)
 #pragma unroll
@@ -827,14 +849,12 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     nu[r] = keep ? xs[r] : xs[r] * 0.0;
                 }
                 if (do_bow) {
-                    // v_rel of the last pass (bow.cpp:35-38): sum rc_i ((u_i - u1_i)/k - v_b) over the window rows
-                    bow_window();
+                    // v_rel of the last pass: sum rc_i ((u_i - u1_i)/k - v_b), rc = o / sum|o|  ==  (sum o_i d_i) / (k sum o) - v_b
 #pragma unroll
                     for (int r = 0; r < ET; r++) { const int i = i0row + r; qs[i] = nu[r] - S[u1o + i] * ((i <= N_t) ? 1.0 : 0.0); }
                     __syncwarp();
                     const int wi0 = min(bow_ic + ln, LE - 1), wi1 = min(bow_ic + L + ln, LE - 1);
-                    const double vB = t[T_VB];
-                    vrel = red_sum<L>(bow_o[0] * (qs[wi0] * ik - vB) + bow_o[1] * (qs[wi1] * ik - vB));
+                    bnum = bw0 * qs[wi0] + bw1 * qs[wi1]; bden = fabs(bw0) + fabs(bw1);     // reduced with the readout sums below
                     __syncwarp();
                 }
                 if (do_ham) {
@@ -1002,12 +1022,18 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 }
                 ext2 = ext1; ext1 = WLs;
                 if (surf) {
-                    zo = red_sum<L>(acc);
                     double au = 0.0;
 #pragma unroll
                     for (int r = 0; r < ET; r++) au += (nu[r] - S[u1o + i0row + r]) * rdw;
-                    uo = red_sum<L>(au);
+                    // one butterfly for all sums of the step (independent shuffles overlap)
+#pragma unroll
+                    for (int o = L / 2; o > 0; o >>= 1) {
+                        acc += __shfl_xor_sync(FULLMASK, acc, o, L); au += __shfl_xor_sync(FULLMASK, au, o, L);
+                        if (!GROUPED) { bnum += __shfl_xor_sync(FULLMASK, bnum, o, L); bden += __shfl_xor_sync(FULLMASK, bden, o, L); }
+                    }
+                    zo = acc; uo = au;
                 } else {
+                    if (!GROUPED) { bnum = red_sum<L>(bnum); bden = red_sum<L>(bden); }
                     __syncwarp();
                     const double rp = cst[C_RP];
                     const int ui = 1 + (int)floor(__dmul_rn((double)N_t, rp));
@@ -1019,6 +1045,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     const double za = (zi < WLa) ? Lb[zno + zi] : 0.0, zb = (zi + 1 < WLa) ? Lb[zno + zi + 1] : 0.0;
                     zo = (1 - zf) * za + zf * zb;
                 }
+                if (!GROUPED && do_bow) vrel = (bnum * A.ik) / bden - t[T_VB];      // empty window: 0/0 = NaN like the reference
                 // state rows: state[:, n] += u  (in place, onto pre-loaded content; string.cpp:264-265)
                 if (save_state) {
                     double *su = (double *)a.state_u.ptr + (int64_t)b * a.state_u.bs + (int64_t)n * a.state_u.ts;
@@ -1136,12 +1163,10 @@ struct Config { int L, ET, maxt; bool grouped; int tier; void (*kern)(const KArg
 #define CFG_I(L_, ET_, MB_, TIER_) Config{L_, ET_, 128, false, TIER_, sfdtd_step_kernel<L_, ET_, false, 128, MB_>}
 #define CFG_G(L_, ET_, MT_) Config{L_, ET_, MT_, true, 0, sfdtd_step_kernel<L_, ET_, true, MT_, 1>}
 // smallest first.  independent mode: <=128-thread CTAs, a string needs rows <= L*ET; tier = register budget variant
-// (0: up to 255/168 registers, 1: 168 everywhere, 2: 128 for the 4-row kernels; SFDTD_TIER selects, default below).
+// (only tier 0 is built: 6/8-row kernels up to 255 registers, 4-row kernels 168; tighter caps measured slower).
 // grouped mode: one CTA per group, needs rows <= L*ET and ceil32(G*L) <= maxt.
 const Config g_configs[] = {
     CFG_I(8, 4, 3, 0), CFG_I(8, 6, 2, 0), CFG_I(16, 4, 3, 0), CFG_I(16, 6, 2, 0), CFG_I(32, 4, 3, 0), CFG_I(32, 8, 1, 0),
-    CFG_I(8, 4, 3, 1), CFG_I(8, 6, 3, 1), CFG_I(16, 4, 3, 1), CFG_I(16, 6, 3, 1), CFG_I(32, 4, 3, 1), CFG_I(32, 8, 2, 1),
-    CFG_I(8, 4, 4, 2), CFG_I(8, 6, 3, 2), CFG_I(16, 4, 4, 2), CFG_I(16, 6, 3, 2), CFG_I(32, 4, 4, 2), CFG_I(32, 8, 2, 2),
     CFG_G(8, 4, 256), CFG_G(8, 6, 256), CFG_G(16, 4, 512), CFG_G(16, 6, 384), CFG_G(32, 4, 1024), CFG_G(32, 8, 128), CFG_G(32, 8, 512),
 };
 constexpr int DEFAULT_TIER = 0;
@@ -1243,6 +1268,9 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     if (a.Nt <= 2) return SFDTD_OK;
 
     cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const auto t_host0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count(); };
+    double t_pre = 0, t_launch = 0;
     int rc = SFDTD_OK, dev = 0;
     bool locked = false;
     const int n_groups = (a.B + a.group_size - 1) / a.group_size;
@@ -1255,6 +1283,9 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     std::map<std::pair<int, int>, Bucket> buckets;      // (config index, WLp) -> items
     std::vector<int32_t> h_ids;
     size_t n_ids_total = 0;
+    struct TimedBucket { int cfg, WLp, items, threads, grid; cudaEvent_t e0, e1; };
+    std::vector<TimedBucket> timed;
+    const bool verbose = getenv("SFDTD_VERBOSE") != nullptr;
     const bool skip_aux = a.flags & SFDTD_SKIP_AUX;
     const int tier = getenv("SFDTD_TIER") ? std::min(2, std::max(0, atoi(getenv("SFDTD_TIER")))) : DEFAULT_TIER;
 
@@ -1286,6 +1317,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     CK(cudaMemcpyAsync(h_bow.data(), a.bow_mask, a.B, cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(h_ham.data(), a.hammer_mask, a.B, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    t_pre = host_ms();
 
     for (int g = 0; g < n_groups; g++) {
         const int g0 = g * a.group_size, G = std::min(a.group_size, a.B - g0);
@@ -1357,14 +1389,15 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
         }
         if (!g_fork_event) CK(cudaEventCreateWithFlags(&g_fork_event, cudaEventDisableTiming));
         CK(cudaEventRecord(g_fork_event, stream));
-        // launch order: largest buckets first
+        // launch order: smallest buckets first.  Every CTA lives for the whole time loop, so a small bucket started late
+        // would trail the bulk by a full CTA lifetime on a nearly empty GPU; started first it overlaps with the bulk.
         typedef std::pair<const std::pair<int, int>, Bucket> BK;
         std::vector<BK *> order;
         for (auto &kv : buckets) order.push_back(&kv);
         std::stable_sort(order.begin(), order.end(), [&](const BK *x, const BK *y) {
             const Config &cx = g_configs[x->first.first], &cy = g_configs[y->first.first];
             (void)cx; (void)cy;
-            return x->second.ids.size() > y->second.ids.size();
+            return x->second.ids.size() < y->second.ids.size();
         });
         int bi = 0;
         for (BK *pkv : order) {
@@ -1407,14 +1440,31 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
             K.ids = d_ids + off; K.n_items = n_items; K.WLp = WLp; K.need_xax = need_xax ? 1 : 0;
             cudaStream_t s = (nb > 1) ? g_side_streams[bi] : stream;
             if (nb > 1) CK(cudaStreamWaitEvent(s, g_fork_event, 0));
+            if (verbose) {
+                TimedBucket tb; tb.cfg = kv.first.first; tb.WLp = WLp; tb.items = n_items; tb.threads = threads; tb.grid = grid;
+                CK(cudaEventCreate(&tb.e0)); CK(cudaEventCreate(&tb.e1));
+                CK(cudaEventRecord(tb.e0, s));
+                timed.push_back(tb);
+            }
             cf.kern<<<(unsigned)grid, threads, sm, s>>>(K);
+            if (verbose) CK(cudaEventRecord(timed.back().e1, s));
             g_launches++;
             CK(cudaGetLastError());
             if (nb > 1) { CK(cudaEventRecord(g_side_events[bi], s)); CK(cudaStreamWaitEvent(stream, g_side_events[bi], 0)); }
             bi++;
         }
     }
+    t_launch = host_ms();
     CK(cudaStreamSynchronize(stream));
+    if (verbose) fprintf(stderr, "[sfdtd] host: prepass+readback %.1f ms, bucketing+launch %.1f ms, total %.1f ms\n", t_pre, t_launch - t_pre, host_ms());
+    for (auto &tb : timed) {
+        float ms = 0, ms0 = 0;
+        cudaEventElapsedTime(&ms, tb.e0, tb.e1); cudaEventElapsedTime(&ms0, timed[0].e0, tb.e1);
+        const Config &cf = g_configs[tb.cfg];
+        fprintf(stderr, "[sfdtd] timing L=%d ET=%d %s WLp=%d items=%d threads=%d grid=%d: %.1f ms (ends at %.1f ms)\n", cf.L, cf.ET,
+                cf.grouped ? "grouped" : "indep", tb.WLp, tb.items, tb.threads, tb.grid, ms, ms0);
+    }
+    for (auto &tb : timed) { cudaEventDestroy(tb.e0); cudaEventDestroy(tb.e1); }
 done:
     if (rc != SFDTD_OK) cudaDeviceSynchronize();
     if (locked) g_stream_mu.unlock();
