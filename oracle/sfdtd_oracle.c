@@ -627,6 +627,20 @@ int sfdtd_oracle_forward(sfdtd_oracle_args *a)
                         for (int i = 0; i < R; i++) uu[i] = -w->rhs[i] - kz[i];
                         thomas(ta, tb, tc, uu, cp, R);
                         for (int i = R; i < Wt; i++) uu[i] = 0.0;
+                        if (getenv("SFDTD_AA")) {
+                            /* experiment: Anderson(1) mixing of the transverse iterate */
+                            static __thread double fprev[4096], gprev[4096];
+                            double num = 0, den = 0;
+                            if (sweeps >= 1) {
+                                for (int i = 0; i < R; i++) { const double f = uu[i] - uo[i], df = f - fprev[i]; num += f * df; den += df * df; }
+                            }
+                            const double gam = (sweeps >= 1 && den > 0) ? num / den : 0.0;
+                            for (int i = 0; i < R; i++) {
+                                const double g_ = uu[i], f = uu[i] - uo[i];
+                                if (sweeps >= 1) uu[i] = g_ - gam * (g_ - gprev[i]);
+                                fprev[i] = f; gprev[i] = g_;
+                            }
+                        }
                         if (phi_ != 0.0) apply_Klt(w, Wt, Wl, phi_, uu, kl, sc1);
                         else for (int j = 0; j < Wl; j++) kl[j] = 0.0;
                         for (int j = 0; j < WLs; j++) {
@@ -651,6 +665,8 @@ int sfdtd_oracle_forward(sfdtd_oracle_args *a)
                         const double estz = dz * rho / (1 - rho);
                         if (getenv("SFDTD_TRACE") && n == atoi(getenv("SFDTD_TRACE")) && b < 6)
                             fprintf(stderr, "n=%d b=%d sweep=%d du/su=%.2e dz/sz=%.2e rho=%.3f est=%.2e estz=%.2e\n", n, b, sweeps, du / su_, dz / sz_, rho, est / su_, estz / sz_);
+                        if (getenv("SFDTD_NOZ")) { if (sweeps >= 3 && !(est > TOL * su_)) break; }
+                        else
                         if (sweeps >= minS && !(est > TOL * su_) && !(estz > TOL * sz_)) break;      /* also exits on NaN */
                         if (sweeps >= 500) { status = 2; break; }
                     }
