@@ -100,8 +100,9 @@ typedef struct sfdtd_args {
     sfdtd_array uout, zout, v_r, F_H, u_H_out;   /* u_H_out = u_H / k (simulator.cpp:57) */
     /* outputs (B): loss parameters of the last step (string.cpp:119-120) */
     void *sig0, *sig1;
-    uint32_t *status;      /* (B) status bits, may be NULL */
-    /* optional (may be NULL): per-string int64[4] counters {outer iterations, linear sweeps, hammer iterations, steps} */
+    uint32_t *status;      /* (B) status bits, OR-ed into the array (zero it before the call), may be NULL */
+    /* optional (may be NULL): per-string int64[4] counters {outer iterations, linear sweeps, hammer iterations, steps},
+       added to the array (zero it before the call) */
     int64_t *counters;
 } sfdtd_args;
 

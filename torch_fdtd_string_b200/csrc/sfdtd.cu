@@ -302,6 +302,25 @@ template <int L, int ET> struct TriSolver {
     }
 };
 
+// manufactured-solution forcing (vnv.cpp:11-37) times k^2, split into the per-step part (MsStep) and the per-row part
+struct MsStep { double c1, c2, c3, ect, est; };
+__device__ __forceinline__ MsStep ms_step(double gamma, double sig0, double K, double p_a, double t, double k2) {
+    MsStep m;
+    const double sigma = sig0, omega = gamma, mu_sq = M_PI * M_PI;
+    m.c1 = sigma * sigma - omega * omega - (2 * sig0) * sigma;
+    m.c2 = (2 * mu_sq) * ((4 * (K * K)) * mu_sq + gamma * gamma);
+    m.c3 = (2 * omega) * (sigma - sig0);
+    const double e = (p_a * exp(-sigma * t)) * k2;
+    m.ect = e * cos(omega * t); m.est = e * sin(omega * t);
+    return m;
+}
+// x: position of padded row i on the reference's domain_x axis (misc.cpp:45-52): clamp(i * 2/N_t, 0, 2), then (v - 1) / 2
+__device__ __forceinline__ double ms_row(const MsStep &m, int i, double two_ht) {
+    const double xv = (fmin(fmax((double)i * two_ht, 0.0), 2.0) - 1.0) * 0.5;
+    const double cx = cos(M_PI * xv), c2x = cos((2 * M_PI) * xv);
+    return (m.c1 * (cx * cx) + m.c2 * c2x) * m.ect + (m.c3 * (cx * cx)) * m.est;
+}
+
 // float32 linear-interpolation row (misc.cpp:78-105; F.interpolate(..., 'linear', align_corners=True) on float32)
 __device__ __forceinline__ void interp_row(float s, int o, int in_last, int &i0, int &i1, float &w0, float &w1) {
     const float r = __fmul_rn(s, (float)o);
@@ -369,6 +388,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
     const bool surf = a.flags & SFDTD_SURFACE_INTEGRAL;
     const bool save_state = a.flags & SFDTD_SAVE_STATE;
     const bool skip_aux = a.flags & SFDTD_SKIP_AUX;
+    const bool manuf = a.flags & SFDTD_MANUFACTURED;
     uint32_t status = 0;
 
     // ---- shared memory carve-up: [bow axis][fixed slot parts][longitudinal parts] ----
@@ -516,6 +536,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 // rows that are solved: R (see header); forced rows of a bowed string extend it
                 int R = N_t + 3;
                 if (bowm) { const int Rb = (int)fmin(fmax(ceil((ctr + wid * 0.5) * Nd) + 1, 0.0), 60000.0); R = max(R, Rb); }
+                if (a.flags & SFDTD_MANUFACTURED) R = Wt;          // every padded row is forced (string.cpp:227-232)
                 R = min(R, Wt);
                 int oob = 0;
                 if (R > LE) { R = LE; oob = 1; }
@@ -644,6 +665,17 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 #pragma unroll
                     for (int r = 0; r < ET; r++) rt[r] = (i0row + r < Rk) ? (rt[r] + (nub[r] - nub[r + 1])) : 0.0;
                 }
+                // manufactured solution (string.cpp:227-232): RHS -= f k^2 on every padded row, before the flat mask
+                MsStep ms;
+                if (manuf) {
+                    const float tf = (float)(n + a.n_0) * a.k;                    // float32 product (string.cpp:229)
+                    const double gamma = 2.0 * ldx(a.f0, b, n);
+                    ms = ms_step(gamma, t[T_S0K] / (2.0 * A.k), gamma * lds(a.kappa, b), lds(a.p_a, b), (double)tf, A.k2);
+                    const int Rk = tabi[jj * NI + I_RK];
+                    const double two_ht = 2.0 / t[T_IHT];
+#pragma unroll
+                    for (int r = 0; r < ET; r++) if (i0row + r < Rk) rt[r] -= ms_row(ms, i0row + r, two_ht);
+                }
                 // A11 (string.cpp:153-162), rows < R, tail folded into row R-1
                 {
                     const double offA = t[T_OFFA], diagA = t[T_DIAGA], corr = t[T_CORR];
@@ -685,6 +717,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                             const double pj1 = LW[2 * j + 2] * qs[li1 & 0xffff] + LW[2 * j + 3] * qs[li1 >> 16];
                             v = dB * z1c + eB * (z1l + z1r) + dC * z2c + eC * (z2l + z2r) - phl * (pj1 - pj);
                         }
+                        // longitudinal rows sit at padded index Nx_t1 + j >= N_t + 1: x clamps to the right end
+                        if (manuf && j < keep_l && j < WLs) v -= ms_row(ms, NXT + j, 2.0 / t[T_IHT]);
                         Lb[rlo + j] = v;
                     }
                 }
@@ -1260,7 +1294,6 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     const sfdtd_args &a = *args;
     if (a.abi_version != SFDTD_ABI_VERSION) { snprintf(g_err, sizeof g_err, "abi_version %d != %d", a.abi_version, SFDTD_ABI_VERSION); return SFDTD_ERR_ARG; }
     if (a.dtype != SFDTD_F64) { snprintf(g_err, sizeof g_err, "only SFDTD_F64 is built"); return SFDTD_ERR_UNSUPPORTED; }
-    if (a.flags & SFDTD_MANUFACTURED) { snprintf(g_err, sizeof g_err, "SFDTD_MANUFACTURED is not built yet"); return SFDTD_ERR_UNSUPPORTED; }
     if (a.B <= 0 || a.group_size <= 0 || a.Nt < 0 || a.Nx_t1 <= 0 || a.Nx_l1 <= 0) { snprintf(g_err, sizeof g_err, "bad sizes"); return SFDTD_ERR_ARG; }
     const void *req[] = {a.state_u.ptr, a.state_z.ptr, a.kappa.ptr, a.alpha.ptr, a.f0.ptr, a.pos.ptr, a.T60.ptr, a.x_b.ptr, a.v_b.ptr,
                          a.F_b.ptr, a.wid.ptr, a.phi_0.ptr, a.phi_1.ptr, a.x_H.ptr, a.w_H.ptr, a.M_r.ptr, a.alpha_H.ptr, a.u_H.ptr,

@@ -72,7 +72,7 @@ def _call(args, stream=None):
 def step_strings(state_u, state_z, *, kappa, alpha, f0, pos, T60, x_b, v_b, F_b, wid, phi_0, phi_1,
                  x_H, w_H, M_r, alpha_H, u_H, bow_mask, hammer_mask, k, theta_t, lambda_c,
                  relative_order, Nt, group_size, surface_integral=True, save_state=False, skip_aux=False,
-                 n_0=0, p_a=None, max_iter=1000, out=None, counters=False, stream=None, check=True):
+                 manufactured=False, n_0=0, p_a=None, max_iter=1000, out=None, counters=False, stream=None, check=True):
     """Native API.  All tensors are float64 CUDA tensors.
 
     state_u/state_z: (B, Nt, Nx) when ``save_state`` (reference layout, updated in place), else
@@ -104,7 +104,7 @@ def step_strings(state_u, state_z, *, kappa, alpha, f0, pos, T60, x_b, v_b, F_b,
     a.abi_version = _lib.SFDTD_ABI_VERSION
     a.dtype = _lib.SFDTD_F64
     a.flags = ((_lib.SURFACE_INTEGRAL if surface_integral else 0) | (_lib.SAVE_STATE if save_state else 0)
-               | (_lib.SKIP_AUX if skip_aux else 0))
+               | (_lib.SKIP_AUX if skip_aux else 0) | (_lib.MANUFACTURED if manufactured else 0))
     a.B, a.group_size, a.Nt, a.Nx_t1, a.Nx_l1 = B, int(group_size), int(Nt), Nx_t1, Nx_l1
     a.n_0, a.max_iter = int(n_0), int(max_iter)
     a.k, a.theta_t, a.lambda_c, a.relative_order = float(k), float(theta_t), float(lambda_c), float(relative_order)
@@ -150,8 +150,6 @@ def forward_fn(state_u, state_z, string_params, bow_params, hammer_params,
     tensors are widened on entry and rounded on exit), results are returned on CUDA like the
     reference's ``device()`` (misc.cpp:13-15) does when a GPU is visible.
     """
-    if manufactured:
-        raise NotImplementedError("manufactured-solution mode is not built yet (SURVEY N4)")
     if not torch.cuda.is_available():
         raise RuntimeError("torch_fdtd_string_b200.forward_fn needs a CUDA device (no CPU fallback)")
     dev = state_u.device if state_u.device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
@@ -181,7 +179,7 @@ def forward_fn(state_u, state_z, string_params, bow_params, hammer_params,
         x_H=D(x_H), w_H=D(w_H), M_r=D(M_r), alpha_H=D(alpha_H), u_H=uH,
         bow_mask=bow_mask, hammer_mask=hammer_mask,
         k=constant[0], theta_t=constant[1], lambda_c=constant[2], relative_order=relative_error,
-        Nt=Nt, group_size=B, surface_integral=bool(surface_integral), save_state=True, n_0=n_0,
+        Nt=Nt, group_size=B, surface_integral=bool(surface_integral), save_state=True, manufactured=bool(manufactured), n_0=n_0,
         p_a=D(p_a))
     # in-place side effects of the reference (string.cpp:264-265, 303)
     if su_cp: state_u.copy_(su)
