@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsfdtd.so")
+LIB_PATH = os.environ.get("SFDTD_LIB") or os.path.join(HERE, "libsfdtd.so")     # SFDTD_LIB: A/B builds of the same ABI
 
 SFDTD_ABI_VERSION = 1
 SFDTD_F64 = 0

@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
     const bool surf = a.flags & SFDTD_SURFACE_INTEGRAL;
     const bool save_state = a.flags & SFDTD_SAVE_STATE;
     const bool skip_aux = a.flags & SFDTD_SKIP_AUX;
-    const bool manuf = a.flags & SFDTD_MANUFACTURED;
+    // the manufactured-solution mode (B = 1 verification runs) is compiled into the grouped kernels only
+    const bool manuf = GROUPED && (a.flags & SFDTD_MANUFACTURED);
     uint32_t status = 0;
 
     // ---- shared memory carve-up: [bow axis][fixed slot parts][longitudinal parts] ----
@@ -1358,7 +1359,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
         bool forced = false;
         int Wt = 0, rows_g = 0;
         for (int s = 0; s < G; s++) {
-            forced = forced || h_bow[g0 + s] || h_ham[g0 + s];
+            forced = forced || h_bow[g0 + s] || h_ham[g0 + s] || (a.flags & SFDTD_MANUFACTURED);
             Wt = std::max(Wt, h_max[g0 + s] + 1);
         }
         for (int s = 0; s < G; s++) {
