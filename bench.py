@@ -269,9 +269,9 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": string_seconds / float(te), "unit": "string-seconds/s",
-               "h2d_bytes_per_step": sampler.compact_nbytes(p_host), "d2h_bytes_per_step": 2 * B * (Nt - 2) * 8,
+               "h2d_bytes_per_step": world * sampler.compact_nbytes(p_host), "d2h_bytes_per_step": world * 2 * B * (Nt - 2) * 8,
                "ms_per_step": float(te) * 1e3,
-               "note": "pinned host compact parameters -> H2D -> on-device control expansion -> stepper -> D2H of uout,zout"}
+               "note": "all ranks: pinned host compact parameters -> H2D -> on-device control expansion -> stepper -> D2H of uout,zout"}
 
     if rank != 0:
         if world > 1:
