@@ -119,3 +119,18 @@ def test_groups_do_not_interact(batch):
     q = torch.quantile(err, torch.tensor([0.5, 0.9], dtype=torch.float64, device=err.device))
     print("group independence: median %.2e  q90 %.2e  max %.2e" % (float(q[0]), float(q[1]), float(err.max())))
     assert float(q[0]) < 1e-12 and float(q[1]) < 1e-9 and float((err > 1e-6).double().mean()) < 0.03
+
+
+def test_mixed_excitation_groups_do_not_spin():
+    """Bowed / hammered / plucked strings mixed in every group (excitation = 'random', src/utils/misc.py:110-120), incl.
+    strings that blow up: the group fixed-point loop must end by convergence (never by its cap), in ~2 passes per step."""
+    from torch_fdtd_string_b200 import sampler
+    p_host = sampler.sample_nsynth_like(48 * GROUP, length=1.0, excitation="random", seed=99)
+    res = run_cuda(p_host, 2402)
+    st = res["status"].cpu()
+    assert int((st & (2 | 4 | 8 | 16)).max()) == 0, sorted(set(st.tolist()))        # outer cap, hammer cap, bow window, range
+    c = res["counters"].double()
+    outer = float(c[:, 0].sum() / c[:, 3].sum())
+    assert 1.9 < outer < 3.0, outer
+    forced = (p_host["bow_mask"] | p_host["hammer_mask"]).cuda()
+    assert torch.isfinite(res["uout"][forced][:, 2:]).all()

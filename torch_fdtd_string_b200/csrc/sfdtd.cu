@@ -731,6 +731,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 #pragma unroll
             for (int r = 0; r < ET; r++) xs[r] = 0.0;
             int zfo = z1o;
+            bool capped = false;                 // the block iteration of this step was cut at GS_CAP (diverging string)
             // All strings of a warp sweep until every one of them has converged (extra sweeps only tighten a
             // converged string), so the loop body carries no per-string predication.
             auto gs_solve = [&](const double (&mr)[ET], bool need, bool first) {
@@ -763,12 +764,15 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     ts.solve(d, ln);
                     // max-norms of the change and of the solution, tracked on the high words of the doubles
                     // (monotone in |x|, 2^-20 resolution; NaN/inf sort above every finite value)
+                    // (grouped mode: a string that needs no new solve in this pass rides along without changing its state --
+                    // re-iterating a diverging string would move it and keep the group's fixed-point loop spinning)
+                    const bool upd = !GROUPED || need;
                     unsigned du = 0u, su = 0u;
 #pragma unroll
                     for (int r = 0; r < ET; r++) {
                         du = max(du, hi_abs(d[r] - xs[r]));
                         if (sweeps == 0) su = max(su, hi_abs(d[r]));
-                        xs[r] = d[r];
+                        if (upd) xs[r] = d[r];
                     }
                     // q = mu (x_i - x_{i-1})  (the scale phi/h_t^2 and the 1/h_t of Dxb are folded into T_PHL)
                     double xl = shup<L>(xs[ET - 1], 1);
@@ -776,7 +780,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 #pragma unroll
                     for (int r = 0; r < ET; r++) qs[i0row + r] = mu[r] * (xs[r] - (r == 0 ? xl : xs[r - 1]));
                     __syncwarp();
-                    for (int j = ln; j <= WLs; j += L) {
+                    if (upd) for (int j = ln; j <= WLs; j += L) {
                         const int li = LI[j];
                         const double2 w = *(const double2 *)(LW + 2 * j);
                         Lb[po + j] = w.x * qs[li & 0xffff] + w.y * qs[li >> 16];
@@ -784,7 +788,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     __syncwarp();
                     {
                         const double PHL = t[T_PHL], idA = t[T_IDA], eidA = t[T_EIDA];
-                        for (int j = ln; j < WLs; j += L) {
+                        if (upd) for (int j = ln; j < WLs; j += L) {
                             double rhs = PHL * (Lb[po + j + 1] - Lb[po + j]);
                             if (j < keep_l) rhs -= Lb[rlo + j];
                             const double zr = (j + 1 < WLs) ? Lb[zco + j + 1] : 0.0;
@@ -792,7 +796,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         }
                     }
                     __syncwarp();
-                    zco = zno;
+                    if (upd) zco = zno;
                     sweeps++;
                     bool ok;
                     if (sweeps == 1) {
@@ -816,7 +820,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         ok = (sweeps >= minS) && !(est > GS_TOL);
                         if (!(e < INFINITY)) ok = true;
                         e_prev = e;
-                        if (!conv && sweeps >= GS_CAP && !ok) { status |= SFDTD_ST_SOLVER_CAP; ok = true; }
+                        if (!conv && sweeps >= GS_CAP && !ok) { status |= SFDTD_ST_SOLVER_CAP; capped = true; ok = true; }
                     }
                     if (!conv) { cnt_sweeps += 1; conv = ok; }
                 } while (__any_sync(FULLMASK, !conv));
@@ -1027,7 +1031,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     nan_u = red_or<L>(nan_u); nan_z = red_or<L>(nan_z);
                     nc_t = red_or<L>(nc_t);
                     nc_l = red_or<L>(nc_l);
-                    const int not_conv = (nc_t && !nan_u) || (nc_l && !nan_z);
+                    // a string whose linear iteration diverges has no fixed point to wait for: it does not vote
+                    const int not_conv = !capped && ((nc_t && !nan_u) || (nc_l && !nan_z));
                     iter++;
                     int more = __syncthreads_or(valid && not_conv);
                     if (iter >= A.max_iter) { if (more) status |= SFDTD_ST_OUTER_CAP; more = 0; }
@@ -1199,13 +1204,16 @@ struct Config { int L, ET, maxt; bool grouped; int tier; void (*kern)(const KArg
 #define CFG_I(L_, ET_, MB_, TIER_) Config{L_, ET_, 128, false, TIER_, sfdtd_step_kernel<L_, ET_, false, 128, MB_>}
 #define CFG_G(L_, ET_, MT_) Config{L_, ET_, MT_, true, 0, sfdtd_step_kernel<L_, ET_, true, MT_, 1>}
 // smallest first.  independent mode: <=128-thread CTAs, a string needs rows <= L*ET; tier = register budget variant
-// (only tier 0 is built: 6/8-row kernels up to 255 registers, 4-row kernels 168; tighter caps measured slower).
+// (tier 2, the default: 16 lanes x 4 rows for every string up to 64 rows, then 32x4, 32x8 -- measured fastest; tier 0 also
+// uses the 8-lane kernels, for A/B runs via SFDTD_TIER=0; 2- and 3-row kernels, tighter register caps (128) and a
+// REDUX-based max reduction all measured slower).
 // grouped mode: one CTA per group, needs rows <= L*ET and ceil32(G*L) <= maxt.
 const Config g_configs[] = {
     CFG_I(8, 4, 3, 0), CFG_I(8, 6, 2, 0), CFG_I(16, 4, 3, 0), CFG_I(16, 6, 2, 0), CFG_I(32, 4, 3, 0), CFG_I(32, 8, 1, 0),
+    CFG_I(16, 4, 3, 2), CFG_I(32, 4, 3, 2), CFG_I(32, 8, 1, 2),
     CFG_G(8, 4, 256), CFG_G(8, 6, 256), CFG_G(16, 4, 512), CFG_G(16, 6, 384), CFG_G(32, 4, 1024), CFG_G(32, 8, 128), CFG_G(32, 8, 512),
 };
-constexpr int DEFAULT_TIER = 0;
+constexpr int DEFAULT_TIER = 2;
 constexpr int N_CONFIGS = sizeof(g_configs) / sizeof(g_configs[0]);
 
 // longitudinal allocation classes of the independent mode (rows incl. the two guards)
@@ -1368,7 +1376,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
             if (!forced) {
                 // lanes: enough rows for the transverse block, and enough lanes that the longitudinal loops stay short
                 const int wlc = wl_class(long_rows(h_max[a.B + g0 + s]));
-                const int min_lanes = std::min(32, wlc / 4);
+                const int min_lanes = std::max(std::min(32, wlc / 4), getenv("SFDTD_MIN_LANES") ? atoi(getenv("SFDTD_MIN_LANES")) : 0);
                 int pick = -1;
                 for (int c = 0; c < N_CONFIGS && pick < 0; c++)
                     if (!g_configs[c].grouped && g_configs[c].tier == tier && rows <= g_configs[c].L * g_configs[c].ET &&
