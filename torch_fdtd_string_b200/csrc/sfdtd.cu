@@ -349,7 +349,7 @@ template <int L, int ET> __device__ __forceinline__ double fetch_row(const doubl
 // shared-memory doubles of the fixed part of a string slot, and of its longitudinal part (W rows incl. guards, W even)
 __host__ __device__ inline int slot_fixed_doubles(int L, int ET, bool grouped) {
     const int LE = L * ET;
-    int n = TBS * (grouped ? NV_G : NV_I) + TBS * NI / 2 + TBS * NOUT + NCONST + (LE + 2) + 2 * (LE + 4) + (grouped ? LE : 0);
+    int n = TBS * (grouped ? NV_G : NV_I) + TBS * NI / 2 + TBS * NOUT + NCONST + (LE + L + 2) + 2 * (LE + L + 6) + (grouped ? LE + L : 0);
     n = (n + 1) & ~1;                 // 16-byte aligned slots (int4 / double2 loads)
     if ((n & 15) == 0) n += 2;        // ... that do not start in the same bank
     return n;
@@ -366,7 +366,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
     constexpr int NV = GROUPED ? NV_G : NV_I;
     // fixed slot layout (offsets in doubles)
     constexpr int O_TABI = TB * NV, O_OST = O_TABI + TB * NI / 2, O_CST = O_OST + TB * NOUT, O_QS = O_CST + NCONST;
-    constexpr int O_UA = O_QS + LE + 2 + 2, O_UB = O_UA + LE + 4, O_RC = O_UB + LE + 2;
+    // row arrays (qs, UA, UB, RC) are indexed through PR(): one pad double per ET rows, so that the blocked accesses
+    // "lane l touches rows l*ET + c" fall into distinct banks (stride ET+1 doubles instead of ET)
+    constexpr int O_UA = O_QS + (LE + L + 2) + 4, O_UB = O_UA + (LE + L + 6), O_RC = O_UB + (LE + L + 2);
+    auto PR = [](int i) { return i + (i + ET) / ET - 1; };            // i >= -ET
     extern __shared__ __align__(16) double smem[];
     const sfdtd_args &a = A.a;
     const int tid = threadIdx.x;
@@ -418,8 +421,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
     int *const tabi = (int *)(S + O_TABI);                            // [TB][NI]
     double *const ost = S + O_OST;                                    // [TB][NOUT]
     double *const cst = S + O_CST;                                    // [NCONST]
-    double *const qs = S + O_QS;                                      // [LE + 2]
-    double *const RC = S + O_RC;                                      // [LE] bow weights (grouped mode only)
+    double *const qs = S + O_QS;                                      // [LE + L + 2], PR()-indexed
+    double *const RC = S + O_RC;                                      // [LE + L] bow weights (grouped mode only), PR()-indexed
     double *const LW = Lb + NLA * WLp;                                // [WLp][2] Int_lt weights
     int *const LI = (int *)(LW + 2 * WLp);                            // [WLp]    Int_lt indices i0 | i1 << 16
     // transverse state rows n-1 / n-2 (in S, guards: 2 each side) and longitudinal arrays (in Lb, guard at [-1]); offsets swap
@@ -454,7 +457,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 
     // ---- initial state: rows n-2, n-1 ----
     {
-        for (int j = ln; j < 2 * LE + 10 + (GROUPED ? LE : 0); j += L) S[O_QS + LE + j] = 0.0;      // UA, UB (with guards), RC
+        for (int j = ln; j < 2 + 2 * (LE + L + 6) + (GROUPED ? LE + L : 0); j += L) S[O_QS + LE + L + j] = 0.0;      // UA, UB (with guards), RC
         for (int j = ln; j < NLA * WLp; j += L) Lb[j] = 0.0;
         for (int j = ln; j < WLp; j += L) { LW[2 * j] = 0.0; LW[2 * j + 1] = 0.0; LI[j] = 0; }
         __syncwarp();
@@ -464,8 +467,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 #pragma unroll
         for (int r = 0; r < ET; r++) {
             const int i = ln * ET + r;
-            S[u2o + i] = (i < NXT) ? su[i] : 0.0;
-            S[u1o + i] = (i < NXT) ? su[a.state_u.ts + i] : 0.0;
+            S[u2o + PR(i)] = (i < NXT) ? su[i] : 0.0;
+            S[u1o + PR(i)] = (i < NXT) ? su[a.state_u.ts + i] : 0.0;
         }
         const double *sz = (const double *)a.state_z.ptr + (int64_t)b * a.state_z.bs + row0 * a.state_z.ts;
         for (int j = ln; j < WLa; j += L) {
@@ -602,7 +605,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     int i0 = 0, i1 = 0; float w0 = 0.f, w1 = 0.f;
                     if (j <= N_l) {
                         interp_row(s_lt, j, N_t, i0, i1, w0, w1);
-                        i0 = min(i0, LE - 1); i1 = min(i1, LE - 1);
+                        i0 = PR(min(i0, LE - 1)); i1 = PR(min(i1, LE - 1));      // qs is PR()-indexed
                     }
                     LW[2 * j] = (double)w0; LW[2 * j + 1] = (double)w1; LI[j] = i0 | (i1 << 16);
                 }
@@ -615,15 +618,17 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
             TriSolver<L, ET> ts;
             double mu[ET + 1], rt[ET];
             const int i0row = ln * ET;
+            const int lnp = ln * (ET + 1);
+            auto PRL = [&](int c) { return lnp + c + (c + ET) / ET - 1; };    // PR(i0row + c) with the division folded at compile time
             {
                 double sq[ET + 1];
                 {
                     // masked previous states (mask_1d, string.cpp:129-132): x * 0 keeps NaN like the reference's multiply
                     double e1[ET + 4], e2[ET + 2];
 #pragma unroll
-                    for (int r = 0; r < ET + 4; r++) { const int i = i0row + r - 2; e1[r] = S[u1o + i] * ((i <= N_t) ? 1.0 : 0.0); }
+                    for (int r = 0; r < ET + 4; r++) { const int i = i0row + r - 2; e1[r] = S[u1o + PRL(r - 2)] * ((i <= N_t) ? 1.0 : 0.0); }
 #pragma unroll
-                    for (int r = 0; r < ET + 2; r++) { const int i = i0row + r - 1; e2[r] = S[u2o + i] * ((i <= N_t) ? 1.0 : 0.0); }
+                    for (int r = 0; r < ET + 2; r++) { const int i = i0row + r - 1; e2[r] = S[u2o + PRL(r - 1)] * ((i <= N_t) ? 1.0 : 0.0); }
                     // Lambda = Dxb u1 (string.cpp:152) on the solved rows; mu = phi/h^2 Lambda; sq = phi/h^2 Lambda^2
                     const double iht = t[T_IHT], ph2 = t[T_PH2];
 #pragma unroll
@@ -700,8 +705,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 #pragma unroll
                     for (int r = 0; r < ET; r++) {
                         const int i = i0row + r;
-                        const double a2 = S[u2o + i] * ((i <= N_t) ? 1.0 : 0.0), b2 = S[u2o + i - 1] * ((i - 1 <= N_t) ? 1.0 : 0.0);
-                        qs[i] = mu[r] * (a2 - b2);
+                        const double a2 = S[u2o + PRL(r)] * ((i <= N_t) ? 1.0 : 0.0), b2 = S[u2o + PRL(r - 1)] * ((i - 1 <= N_t) ? 1.0 : 0.0);
+                        qs[PRL(r)] = mu[r] * (a2 - b2);
                     }
                     __syncwarp();
                     const double ihl = t[T_IHL], ihl2 = ihl * ihl, s0k = t[T_S0K], s1k = t[T_S1K], ga2 = t[T_GA2], phl = t[T_PHL];
@@ -778,7 +783,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     double xl = shup<L>(xs[ET - 1], 1);
                     if (ln == 0) xl = 0.0;
 #pragma unroll
-                    for (int r = 0; r < ET; r++) qs[i0row + r] = mu[r] * (xs[r] - (r == 0 ? xl : xs[r - 1]));
+                    for (int r = 0; r < ET; r++) qs[PRL(r)] = mu[r] * (xs[r] - (r == 0 ? xl : xs[r - 1]));
                     __syncwarp();
                     if (upd) for (int j = ln; j <= WLs; j += L) {
                         const int li = LI[j];
@@ -890,18 +895,18 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 if (do_bow) {
                     // v_rel of the last pass: sum rc_i ((u_i - u1_i)/k - v_b), rc = o / sum|o|  ==  (sum o_i d_i) / (k sum o) - v_b
 #pragma unroll
-                    for (int r = 0; r < ET; r++) { const int i = i0row + r; qs[i] = nu[r] - S[u1o + i] * ((i <= N_t) ? 1.0 : 0.0); }
+                    for (int r = 0; r < ET; r++) { const int i = i0row + r; qs[PRL(r)] = nu[r] - S[u1o + PRL(r)] * ((i <= N_t) ? 1.0 : 0.0); }
                     __syncwarp();
                     const int wi0 = min(bow_ic + ln, LE - 1), wi1 = min(bow_ic + L + ln, LE - 1);
-                    bnum = bw0 * qs[wi0] + bw1 * qs[wi1]; bden = fabs(bw0) + fabs(bw1);     // reduced with the readout sums below
+                    bnum = bw0 * qs[PR(wi0)] + bw1 * qs[PR(wi1)]; bden = fabs(bw0) + fabs(bw1);     // reduced with the readout sums below
                     __syncwarp();
                 }
                 if (do_ham) {
                     // un-hammered string: the contact loop runs once with eta = 0 (hammer.cpp:28-53)
                     const int idxH = tabi[jj * NI + I_IDXH];
                     const double mk = (idxH <= N_t) ? 1.0 : 0.0;
-                    const double eta1 = uH1 - S[u1o + idxH] * mk;
-                    const double eta2 = uH2 - S[u2o + idxH] * mk;
+                    const double eta1 = uH1 - S[u1o + PR(idxH)] * mk;
+                    const double eta2 = uH2 - S[u2o + PR(idxH)] * mk;
                     const double r1 = eta1 > 0 ? eta1 : (eta1 != eta1 ? eta1 : 0.0);
                     const double ex = cst[C_AHM1];
                     const double r1pow = (ex == 2.0) ? r1 * r1 : ((ex == 0.0) ? 1.0 : pow(r1, ex));
@@ -922,18 +927,18 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     bow_window();
                     rc_nan = (bow_S == 0.0) || (bow_S != bow_S);             // every weight is NaN (0/0) in the reference
 #pragma unroll
-                    for (int r = 0; r < ET; r++) RC[i0row + r] = 0.0;
+                    for (int r = 0; r < ET; r++) RC[PRL(r)] = 0.0;
                     __syncwarp();
-                    if (bow_ic + ln < LE) RC[bow_ic + ln] = bow_o[0];
-                    if (bow_ic + L + ln < LE) RC[bow_ic + L + ln] = bow_o[1];
+                    if (bow_ic + ln < LE) RC[PR(bow_ic + ln)] = bow_o[0];
+                    if (bow_ic + L + ln < LE) RC[PR(bow_ic + L + ln)] = bow_o[1];
                     __syncwarp();
                 }
                 // hammer: contact point and relative displacements (hammer.cpp:70-74)
                 double eta1 = 0.0, eta2 = 0.0, r1pow = 0.0;
                 if (do_ham) {
                     const double mk = (idxH <= N_t) ? 1.0 : 0.0;
-                    eta1 = uH1 - S[u1o + idxH] * mk;
-                    eta2 = uH2 - S[u2o + idxH] * mk;
+                    eta1 = uH1 - S[u1o + PR(idxH)] * mk;
+                    eta2 = uH2 - S[u2o + PR(idxH)] * mk;
                     const double r1 = eta1 > 0 ? eta1 : (eta1 != eta1 ? eta1 : 0.0);
                     const double ex = cst[C_AHM1];
                     r1pow = (ex == 2.0) ? r1 * r1 : ((ex == 0.0) ? 1.0 : pow(r1, ex));
@@ -941,7 +946,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 const double tol_t = GROUPED ? t[T_TOLT] : 0.0, tol_l = GROUPED ? t[T_TOLL] : 0.0;
                 // the iterate starts as the unmasked state[n-1] (string.cpp:190-191)
 #pragma unroll
-                for (int r = 0; r < ET; r++) nu[r] = S[u1o + i0row + r];
+                for (int r = 0; r < ET; r++) nu[r] = S[u1o + PRL(r)];
                 for (int j = ln; j < WLa; j += L) Lb[zpo + j] = Lb[z1o + j];
                 __syncwarp();
                 int iter = 0;
@@ -956,9 +961,9 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         for (int r = 0; r < ET; r++) {
                             const int i = i0row + r;
                             const double mk = (i <= N_t) ? 1.0 : 0.0;
-                            const double m1 = S[u1o + i] * mk;
-                            const double dd = (iter == 0) ? (m1 - S[u2o + i] * mk) : (nu[r] - m1);
-                            const double rcv = rc_nan ? bow_o[0] : RC[i];
+                            const double m1 = S[u1o + PRL(r)] * mk;
+                            const double dd = (iter == 0) ? (m1 - S[u2o + PRL(r)] * mk) : (nu[r] - m1);
+                            const double rcv = rc_nan ? bow_o[0] : RC[PRL(r)];
                             acc += rcv * (dd * ik - vB);
                         }
                         vrel = red_sum<L>(acc);
@@ -998,7 +1003,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         for (int r = 0; r < ET; r++) {
                             const int i = i0row + r;
                             double f = 0.0;
-                            if (bowm) f += nan0(sB * (rc_nan ? bow_o[0] : RC[i]));
+                            if (bowm) f += nan0(sB * (rc_nan ? bow_o[0] : RC[PRL(r)]));
                             if (hamm && i == idxH) f += sH;
                             mr[r] = (i < Rk) ? rt[r] + f : 0.0;
                         }
@@ -1064,7 +1069,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 if (surf) {
                     double au = 0.0;
 #pragma unroll
-                    for (int r = 0; r < ET; r++) au += (nu[r] - S[u1o + i0row + r]) * rdw;
+                    for (int r = 0; r < ET; r++) au += (nu[r] - S[u1o + PRL(r)]) * rdw;
                     // one butterfly for all sums of the step (independent shuffles overlap)
 #pragma unroll
                     for (int o = L / 2; o > 0; o >>= 1) {
@@ -1102,7 +1107,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     ext1 = WLa;
                 }
 #pragma unroll
-                for (int r = 0; r < ET; r++) S[u2o + i0row + r] = nu[r];
+                for (int r = 0; r < ET; r++) S[u2o + PRL(r)] = nu[r];
                 { const int tmp = u1o; u1o = u2o; u2o = tmp; }
                 z2o = z1o; z1o = zno;
                 __syncwarp();
@@ -1140,7 +1145,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 #pragma unroll
             for (int r = 0; r < ET; r++) {
                 const int i = ln * ET + r;
-                if (i < NXT) { su[i] = S[u2o + i]; su[a.state_u.ts + i] = S[u1o + i]; }
+                if (i < NXT) { su[i] = S[u2o + PR(i)]; su[a.state_u.ts + i] = S[u1o + PR(i)]; }
             }
             double *sz = (double *)a.state_z.ptr + (int64_t)b * a.state_z.bs;
             for (int j = ln; j < WLa; j += L) if (j < NXL) { sz[j] = Lb[z2o + j]; sz[a.state_z.ts + j] = Lb[z1o + j]; }
