@@ -4,6 +4,8 @@ reference batches of 24, the compact native API, through the C ABI).
 Tolerance (BASELINE.json north_star): relative L2 <= 1e-6 in fp64 -- except on strings whose dynamics amplify a 1-ulp
 perturbation beyond that in the reference scheme itself (DESIGN.md "Sensitivity"); for those the bound is 100x the
 oracle's own sensitivity (dense-LU oracle with the initial state scaled by 1 + 2^-50 vs unscaled)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -134,3 +136,28 @@ def test_mixed_excitation_groups_do_not_spin():
     assert 1.9 < outer < 3.0, outer
     forced = (p_host["bow_mask"] | p_host["hammer_mask"]).cuda()
     assert torch.isfinite(res["uout"][forced][:, 2:]).all()
+
+
+def test_dataset_layout(tmp_path):
+    """Result-file layout of the reference (README "Simulation results", src/utils/misc.py:235-299) from the device-side
+    post-processing: wav triplet + four archives per kept string; NaN / silent strings are dropped."""
+    import wave
+    from torch_fdtd_string_b200 import dataset
+    st = dataset.generate(str(tmp_path), num_samples=48, batch_size=24, excitation="pluck", length=0.05, seed=5)
+    assert st["strings"] == 48 and st["written"] == 48 - st["nan"] - st["silent"] and st["written"] > 30
+    dirs = sorted(os.listdir(tmp_path))
+    assert len(dirs) == st["written"]
+    d = tmp_path / dirs[0]
+    assert sorted(os.listdir(d)) == ["bow_params.npz", "hammer_params.npz", "output-u.wav", "output-z.wav", "output.wav",
+                                     "simulation.npz", "simulation_config.yaml", "string_params.npz"]
+    w = wave.open(str(d / "output-u.wav"))
+    assert (w.getframerate(), w.getnframes(), w.getsampwidth()) == (48000, 2400 - 2, 3)          # PCM_24 for double
+    frames = np.frombuffer(w.readframes(w.getnframes()), dtype=np.uint8).reshape(-1, 3).astype(np.int64)
+    v = frames[:, 0] | (frames[:, 1] << 8) | (frames[:, 2] << 16)
+    v = np.where(v >= 1 << 23, v - (1 << 24), v)
+    assert abs(np.abs(v).max() - 8388607) <= 1                                                   # l-infinity normalised
+    sim = np.load(d / "simulation.npz")
+    assert set(sim.files) >= {"uout", "zout", "v_r_out", "F_H_out", "u_H_out", "bow_mask", "hammer_mask", "pluck_mask", "Nx_t", "Nx_l", "sig0", "sig1"}
+    assert sim["uout"].shape == (2398,) and bool(sim["pluck_mask"])
+    sp = np.load(d / "string_params.npz")
+    assert set(sp.files) == {"kappa", "alpha", "u0", "v0", "p_a", "f0", "pos", "T60", "target_f0"}

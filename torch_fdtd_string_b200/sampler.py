@@ -188,6 +188,24 @@ def expand_controls(p, device, n_run=None):
     return dict(f0=f0, x_b=x_b, v_b=v_b, F_b=F_b, wid=wid, u_H=u_H)
 
 
+def fletcher_w0(kappa):
+    """stiff-string detune factor f_1 / f0 (reference src/utils/fdm.py:143-158); f0 is pre-corrected by it"""
+    Bc = (math.pi * kappa) ** 2
+    return (1 + (2 / math.pi) * Bc.sqrt() + 4 / math.pi ** 2 * Bc) * (1 + Bc).sqrt()
+
+
+def concat(parts):
+    """concatenates sampler outputs of equal (Nx_t1, Nx_l1, Nt) along the string axis"""
+    p0 = parts[0]
+    for q in parts[1:]:
+        assert (q["Nx_t1"], q["Nx_l1"], q["Nt"]) == (p0["Nx_t1"], p0["Nx_l1"], p0["Nt"])
+    out = dict(p0)
+    for kx in TENSOR_KEYS + ["p_x", "pluck_mask"]:
+        out[kx] = torch.cat([q[kx] for q in parts], 0)
+    out["B"] = sum(q["B"] for q in parts)
+    return out
+
+
 TENSOR_KEYS = ["kappa", "alpha", "pos", "T60", "p_a", "state_u", "state_z", "f0_a", "f0_b", "mod_frq", "mod_amp",
                "vib_t0", "x_H", "v_H", "M_r", "w_H", "alpha_H", "x_b1", "x_b2", "v_b1", "v_b2", "F_b1", "F_b2",
                "pulloff", "phi_0", "phi_1", "wid", "bow_mask", "hammer_mask"]
