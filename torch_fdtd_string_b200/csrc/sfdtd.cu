@@ -814,18 +814,19 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         // error contracts by 2e-5 per sweep), so it needs no criterion of its own.
                         const float e = hi_to_float(red_maxu<L>(du)) * isu;
                         float rho = 2.0f * rho_h;
-                        if (sweeps >= 3 && e_prev > 0.f) {
-                            const float rr = __fdividef(e, e_prev);
-                            if (!conv) rho_h = (rr > rho_h) ? rr : 0.5f * (rho_h + rr);
+                        if (sweeps >= 3) {
+                            // measured contraction rate e / e_prev (e_prev = 0: the iteration had already converged)
+                            const float rr = __fdividef(e, fmaxf(e_prev, 1e-37f));
+                            const float rh = (rr > rho_h) ? rr : 0.5f * (rho_h + rr);
+                            rho_h = conv ? rho_h : rh;
                             rho = 1.5f * rho_h;
                         }
                         rho = fminf(rho, 0.9f);
-                        const float est = e * __fdividef(rho, 1.0f - rho);
-                        const int minS = (keep_l > 0) ? 4 : 3;
-                        ok = (sweeps >= minS) && !(est > GS_TOL);
-                        if (!(e < INFINITY)) ok = true;
+                        // e rho / (1 - rho) <= tol, without the division
+                        ok = (sweeps >= ((keep_l > 0) ? 4 : 3)) && !(e * rho > GS_TOL * (1.0f - rho));
+                        ok = ok || !(e < INFINITY);
                         e_prev = e;
-                        if (!conv && sweeps >= GS_CAP && !ok) { status |= SFDTD_ST_SOLVER_CAP; capped = true; ok = true; }
+                        if (sweeps >= GS_CAP && !ok && !conv) { status |= SFDTD_ST_SOLVER_CAP; capped = true; ok = true; }
                     }
                     if (!conv) { cnt_sweeps += 1; conv = ok; }
                 } while (__any_sync(FULLMASK, !conv));
