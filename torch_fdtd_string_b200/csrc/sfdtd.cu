@@ -4,8 +4,9 @@
 // /root/reference/src/model/cpp/*.cpp):
 //
 //   * Every string is owned by L lanes of one warp for the whole call.  Transverse block: blocked
-//     layout, ET consecutive grid rows per lane; u^{n-1}, u^{n-2}, the tridiagonal factors and the
-//     right-hand side live in registers; stencil halos move with warp shuffles.
+//     layout, ET consecutive grid rows per lane; the state rows u^{n-1}, u^{n-2} live in shared memory
+//     (bank-conflict-free padded rows with guard cells, so stencil halos are plain loads), the per-step
+//     working set (coefficients, tridiagonal factors, right-hand side, iterate) in registers.
 //   * Only the rows that can differ from zero are solved: R = min(W_t, N_t+3) transverse rows.  The
 //     reference solves all W_t = batch-max rows (misc.cpp:119-127); rows >= N_t+3 form a homogeneous
 //     constant-coefficient tail whose exact effect is a continued-fraction correction of the pivot of
@@ -196,11 +197,6 @@ template <int L> __device__ __forceinline__ double red_sum(double v) {
     for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o, L);
     return v;
 }
-template <int L> __device__ __forceinline__ float red_maxf(float v) {
-#pragma unroll
-    for (int o = L / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULLMASK, v, o, L));
-    return v;
-}
 template <int L> __device__ __forceinline__ int red_or(int v) {
 #pragma unroll
     for (int o = L / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(FULLMASK, v, o, L);
@@ -216,12 +212,6 @@ template <int L> __device__ __forceinline__ unsigned red_maxu(unsigned v) {
     for (int o = L / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULLMASK, v, o, L));
     return v;
 }
-// fmaxf drops NaN operands: a NaN anywhere must still end the sweeps, so NaN is mapped to +inf here
-__device__ __forceinline__ float absf_nan_inf(double v) {
-    const float f = fabsf((float)v);
-    return (f != f) ? INFINITY : f;
-}
-
 __device__ __forceinline__ double nan0(double v) {   // nan_to_num (string.cpp:225-226)
     if (v != v) return 0.0;
     if (isinf(v)) return v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
