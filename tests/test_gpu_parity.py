@@ -58,16 +58,20 @@ def test_chunked_equals_unchunked_on_gpu():
         assert gu.rel_l2(a[k].cpu().numpy(), b[k].cpu().numpy()) < 1e-12, k
 
 
-def test_cuda_matches_oracle_on_seeded_groups(oracle):
-    """Several groups in one launch (native API), compact state, vs the C oracle per group."""
+@pytest.mark.parametrize("name,B", [("random_b24", 24), ("random_b24", 20), ("pluck_b24", 21)])
+def test_cuda_matches_oracle_on_seeded_groups(oracle, name, B):
+    """Several groups in one launch (native API), compact state, vs the C oracle per group; B = 20 / 21 leave a short
+    last group (4 / 5 of 8 strings) in the grouped (random) and in the independent (pluck) mode."""
     from torch_fdtd_string_b200 import step_strings
-    g = gu.load_golden("random_b24")
+    g = gu.load_golden(name)
     inp = gu.build_inputs(g)                      # CPU tensors
-    B, Nt = int(g["B"]), 96
+    Nt = 96
+    cutB = lambda t: t[:B] if (isinstance(t, torch.Tensor) and t.dim() > 0 and t.size(0) == int(g["B"])) else t
+    inp = {k: ([cutB(x) for x in v] if isinstance(v, list) and k.endswith("_params") else cutB(v)) for k, v in inp.items()}
     # oracle: three groups of 8 strings, each its own reference batch
     ref = {k: [] for k in KEYS}
     for g0 in range(0, B, 8):
-        sl = slice(g0, g0 + 8)
+        sl = slice(g0, min(g0 + 8, B))
         sub = dict(inp)
         sub["state_u"] = inp["state_u"][sl, :Nt].clone(); sub["state_z"] = inp["state_z"][sl, :Nt].clone()
         sub["string_params"] = [p[sl, :Nt].clone() if (p.dim() > 1 and p.size(1) > 2) else p[sl].clone() for p in inp["string_params"]]
@@ -95,6 +99,6 @@ def test_cuda_matches_oracle_on_seeded_groups(oracle):
     for k in KEYS:
         err = gu.rel_l2(res[m[k]][:, 2:].cpu().numpy(), ref[k])
         print(k, f"{err:.2e}")
-        assert err < TOL_U, (k, err)
+        assert err < (TOL_U if name != "pluck_b24" else 1e-5), (k, err)
     cnt = res["counters"].cpu().numpy()
     assert (cnt[:, 3] == Nt - 2).all()
