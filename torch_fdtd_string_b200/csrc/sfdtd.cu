@@ -1473,6 +1473,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
                 const int per = threads / cf.L; grid = (n_items + per - 1) / per;
                 sm = smem_bytes_indep(cf, threads / cf.L, a.Nx_t1, WLp, need_xax);
             }
+            if (getenv("SFDTD_PAD_SMEM")) sm = std::max(sm, (size_t)atoi(getenv("SFDTD_PAD_SMEM")));    // occupancy experiments
             if (sm > 227 * 1024) {
                 snprintf(g_err, sizeof g_err, "a bucket (L=%d, ET=%d, %s) needs %zu bytes of shared memory (> 227 KB)", cf.L, cf.ET, cf.grouped ? "grouped" : "independent", sm);
                 rc = SFDTD_ERR_UNSUPPORTED; goto done;
