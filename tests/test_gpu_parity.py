@@ -102,3 +102,23 @@ def test_cuda_matches_oracle_on_seeded_groups(oracle, name, B):
         assert err < (TOL_U if name != "pluck_b24" else 1e-5), (k, err)
     cnt = res["counters"].cpu().numpy()
     assert (cnt[:, 3] == Nt - 2).all()
+
+
+def test_single_precision_tensors_are_widened():
+    """The reference's `precision: single` preset hands float32 tensors to forward_fn: the drop-in computes in fp64 and
+    returns float32 (same dtype as the reference would), equal to the fp64 run up to float32 rounding; the in-place
+    state / u_H updates land in the caller's float32 tensors."""
+    from torch_fdtd_string_b200 import forward_fn
+    g = gu.load_golden("random_b6")
+    i64 = gu.build_inputs(g, device="cuda")
+    i32 = gu.build_inputs(g, dtype=torch.float32, device="cuda")
+    args = lambda i: (i["state_u"], i["state_z"], i["string_params"], i["bow_params"], i["hammer_params"], i["bow_mask"],
+                      i["hammer_mask"], i["consts"], i["relative_order"], i["surface_integral"], False, 0, i["Nt"])
+    o64 = forward_fn(*args(i64))
+    o32 = forward_fn(*args(i32))
+    assert o32[0].dtype == torch.float32 and o32[2].dtype == torch.float32
+    assert o32[2].data_ptr() == i32["state_u"].data_ptr()
+    for a, b in zip(o32[:2], o64[:2]):
+        ref = b[:, 2:].float()
+        assert float((a[:, 2:] - ref).norm() / ref.norm()) < 5e-5      # inputs themselves were rounded to float32
+    assert float(i32["state_u"][:, 5].abs().max()) > 0                  # history written in place
