@@ -813,7 +813,9 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         }
                         rho = fminf(rho, 0.9f);
                         // e rho / (1 - rho) <= tol, without the division
-                        ok = (sweeps >= ((keep_l > 0) ? 4 : 3)) && !(e * rho > GS_TOL * (1.0f - rho));
+                        // (a warm-started re-solve of a later fixed-point pass starts from the previous pass's solution: its
+                        // very first change is already a meaningful error measure)
+                        ok = (sweeps >= ((keep_l > 0) ? 4 : (first ? 3 : 2))) && !(e * rho > GS_TOL * (1.0f - rho));
                         ok = ok || !(e < INFINITY);
                         e_prev = e;
                         if (sweeps >= GS_CAP && !ok && !conv) { status |= SFDTD_ST_SOLVER_CAP; capped = true; ok = true; }
@@ -1460,8 +1462,10 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
                 // CTA size that keeps the most strings resident per SM (registers and shared memory both bound it)
                 const int regs = kernel_regs(cf);
                 int best = 32; long best_res = -1;
+                const int th_force = getenv("SFDTD_CTA_THREADS") ? atoi(getenv("SFDTD_CTA_THREADS")) : 0;
                 for (int th : {128, 96, 64, 32}) {
                     if (th % cf.L) continue;
+                    if (th_force && th != std::max(th_force, cf.L)) continue;
                     const size_t b_ = smem_bytes_indep(cf, th / cf.L, a.Nx_t1, WLp, need_xax);
                     if (b_ > 227 * 1024) continue;
                     const long by_smem = (long)((227 * 1024) / (b_ + 1024)), by_regs = 65536 / ((long)regs * th);
