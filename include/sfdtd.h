@@ -79,7 +79,7 @@ typedef struct sfdtd_args {
     int32_t Nt;            /* time samples in this call; steps n = 2 .. Nt-1 are computed (simulator.cpp:40) */
     int32_t Nx_t1, Nx_l1;  /* padded state widths = state_u.size(-1), state_z.size(-1) (string.cpp:123-124) */
     int32_t n_0;           /* global index of local sample 0 (simulator.cpp:26; only used by MANUFACTURED) */
-    int32_t max_iter;      /* cap for the reference's uncapped loops; <=0 -> 1000 */
+    int32_t max_iter;      /* cap for the reference's uncapped loops (string.cpp:200, hammer.cpp:33); <=0 -> 100 */
     /* `constant` and `relative_error` arrive as float32 in the reference (simulator.cpp:22-23) */
     float k, theta_t, lambda_c, relative_order;
 

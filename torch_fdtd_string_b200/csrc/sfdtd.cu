@@ -1339,7 +1339,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     { const float t1 = 2 * a.theta_t - 1; const float t2 = 2 * t1; K.tt1 = (double)t1; K.tt2 = (double)t2; }   // string.cpp:30-31
     K.lamc = (double)a.lambda_c; K.order = (double)a.relative_order;
     K.mhd = (double)(-0.01f);                                                // hammer.cpp:3
-    K.max_iter = a.max_iter > 0 ? a.max_iter : 1000;
+    K.max_iter = a.max_iter > 0 ? a.max_iter : 100;
 
     CK(cudaGetDevice(&dev));
     g_stream_mu.lock(); locked = true;          // scratch buffers and side streams are shared by all callers
