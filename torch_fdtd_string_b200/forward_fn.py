@@ -72,7 +72,7 @@ def _call(args, stream=None):
 def step_strings(state_u, state_z, *, kappa, alpha, f0, pos, T60, x_b, v_b, F_b, wid, phi_0, phi_1,
                  x_H, w_H, M_r, alpha_H, u_H, bow_mask, hammer_mask, k, theta_t, lambda_c,
                  relative_order, Nt, group_size, surface_integral=True, save_state=False, skip_aux=False,
-                 manufactured=False, n_0=0, p_a=None, max_iter=200, out=None, counters=False, stream=None, check=True):
+                 manufactured=False, n_0=0, p_a=None, max_iter=100, out=None, counters=False, stream=None, check=True):
     """Native API.  All tensors are float64 CUDA tensors.
 
     state_u/state_z: (B, Nt, Nx) when ``save_state`` (reference layout, updated in place), else
