@@ -71,7 +71,8 @@ def save_simulation_data(directory, excitation_type, simulation_dict, string_dic
 
 def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000, length=1.0, seed=1234,
              precision="double", normalize_output=True, skip_silence=True, silence_threshold=-23.0, save=True,
-             randomize_name=False, batches_per_call=64, rank=0, world_size=1, device=None, surface_integral=True):
+             randomize_name=False, batches_per_call=64, rank=0, world_size=1, device=None, surface_integral=True,
+             sampler_cfg=None, time_log=False):
     """Generates ``num_samples // batch_size`` reference batches (reference run.py:109) and writes the kept strings.
     Returns dict(strings, written, nan, silent, seconds_stepper)."""
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -87,7 +88,7 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
         # share the padded state widths (they come from the batch's largest stiffness, like in the reference)
         by_width = {}
         for it in mine[c0:c0 + batches_per_call]:
-            q = sampler.sample_nsynth_like(batch_size, sr=sr, length=length, excitation=excitation, seed=seed + it)
+            q = sampler.sample_nsynth_like(batch_size, sr=sr, length=length, excitation=excitation, seed=seed + it, cfg=sampler_cfg)
             by_width.setdefault((q["Nx_t1"], q["Nx_l1"]), []).append((it, q))
         calls += list(by_width.values())
     for group in calls:
@@ -104,6 +105,11 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
         pp = postprocess(uout, zout, silence_threshold, normalize_output)
         torch.cuda.synchronize()
         stats["seconds_stepper"] += e0.elapsed_time(e1) * 1e-3
+        if time_log:
+            # reference src/task/simulate.py:327-328 logs one line per batch; here one stepper call covers several batches
+            with open(f"{save_dir}/gpu_time.txt", "a") as f:
+                for it in chunk:
+                    f.write(f"{it}\t{e0.elapsed_time(e1) * 1e-3 / len(chunk):.4f}\n")
         is_nan = pp["is_nan"].cpu().numpy(); is_silent = pp["is_silent"].cpu().numpy()
         keep = ~is_nan & ~(is_silent & skip_silence)
         stats["strings"] += B; stats["nan"] += int(is_nan.sum()); stats["silent"] += int((is_silent & ~is_nan).sum())

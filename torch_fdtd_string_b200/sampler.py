@@ -23,6 +23,8 @@ NSYNTH = dict(
     x_H_min=0.1, x_H_max=0.9, v_H_min=0.5, v_H_max=5.0, M_r_min=1.0, M_r_max=10.0, w_H_min=1000.0, w_H_max=3000.0,
     alpha_H=3.0, x_b_min=0.2, x_b_max=0.5, x_b_maxdiff=0.2, v_b_min=0.3, v_b_max=0.4, F_b_min=80.0, F_b_max=100.0,
     F_b_maxdiff=10.0, phi_0_min=2.0, phi_0_max=6.0, phi_1_min=0.0, phi_1_max=0.5, wid_min=3.0, wid_max=6.0,
+    # sampling_T60: 'random' | 'fix' (t60_fixed at 1000 / 100 Hz, or lossless = all-zero decay times; simulator.py:376-385)
+    sampling_T60="random", lossless=False, t60_fixed=20.0,
 )
 
 
@@ -64,7 +66,7 @@ def sample_nsynth_like(B, sr=48000, length=1.0, excitation="pluck", seed=1234, c
     g = torch.Generator().manual_seed(seed)
     k = 1.0 / sr
     Nt = int(sr * length)
-    theta_t = get_theta(c["kappa_max"], c["f0_min"], sr)
+    theta_t = c["theta_t"] if c.get("theta_t") is not None else get_theta(c["kappa_max"], c["f0_min"], sr, c["lambda_c"])
     # masks (src/utils/misc.py:95-121)
     if excitation.endswith("bow"):
         bow = torch.ones(B, dtype=torch.bool); ham = torch.zeros(B, dtype=torch.bool)
@@ -101,6 +103,9 @@ def sample_nsynth_like(B, sr=48000, length=1.0, excitation="pluck", seed=1234, c
     T_f2 = fmin + (T_f1 - 1000 - fmin) * torch.rand(B, generator=g, dtype=torch.float64)
     T_t1 = _u(c["t60_min_1"], c["t60_max_1"], B, g)
     T_t2 = (T_t1 + _u(0, c["t60_diff_max"], B, g)).clamp(c["t60_min_2"], c["t60_max_2"])
+    if c["sampling_T60"] == "fix":
+        T_f1 = torch.full((B,), 1000.0, dtype=torch.float64); T_f2 = torch.full((B,), 100.0, dtype=torch.float64)
+        T_t1 = torch.full((B,), 0.0 if c["lossless"] else float(c["t60_fixed"]), dtype=torch.float64); T_t2 = T_t1.clone()
     T60 = torch.stack([torch.stack([T_f1, T_t1], -1), torch.stack([T_f2, T_t2], -1)], 1)   # (B,2,2)
     # pluck shape (simulator.py:169-200; misc.py:60-72 triangular), rows n=0 and n=1 of state_u
     p_a = _u(c["p_a_min"], c["p_a_max"], B, g) * pluck
