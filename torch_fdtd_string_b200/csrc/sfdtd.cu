@@ -63,9 +63,15 @@ constexpr int NOUT = 5;             // staged outputs per step
 constexpr int NCONST = 8;           // per-string constants kept in shared memory
 constexpr int GS_CAP = 60;          // cap on block Gauss-Seidel sweeps per solve
 constexpr float GS_TOL = 1e-13f;    // predicted relative max-norm error of the transverse block that ends the sweeps
-constexpr int NLA_I = 6;            // longitudinal arrays per string, independent mode: Z1 Z2 ZA ZB RL P
-constexpr int NLA_G = 7;            // grouped mode: + ZP (previous fixed-point iterate)
+constexpr int NLA_I = 5;            // longitudinal arrays per string, independent mode: Z1 Z2 ZA ZB RL
+constexpr int NLA_G = 6;            // grouped mode: + ZP (previous fixed-point iterate)
 constexpr int TBS = 8;              // time steps per scalar-table block
+#ifndef SFDTD_PREDICT_SWEEPS
+#define SFDTD_PREDICT_SWEEPS 1
+#endif
+#ifndef SFDTD_DEFAULT_QUEUE
+#define SFDTD_DEFAULT_QUEUE 1
+#endif
 
 // table slots (doubles)
 enum { T_IHT = 0, T_OFFA, T_DIAGA, T_CORR, T_OFFC, T_DIAGC, T_DIAGB, T_OFF1B, T_KH4, T_PH2, T_PHL, T_IDA, T_EIDA,
@@ -88,6 +94,10 @@ struct KArgs {
     int32_t need_xax;               // copy the bow axis to shared memory
     int32_t max_iter;
     int32_t n_lo, n_hi;             // time slice of this launch: steps n_lo <= n < n_hi (2 <= n_lo)
+    int32_t *queue;                 // independent mode, optional: work counter; every warp pulls its next (time slice, set of 32/L strings) from it
+    int32_t *done;                  // queue mode: per set, the number of time slices completed (release/acquire hand-over of the state rows)
+    int32_t q_slice, q_nslices;     // queue mode: steps per time slice, number of slices (of the sets beyond q_full)
+    int32_t q_full;                 // queue mode: the first q_full sets run the whole call as one item
 };
 
 __device__ __forceinline__ double ldx(const sfdtd_array &A, int b, int n) {
@@ -202,6 +212,10 @@ template <int L> __device__ __forceinline__ int red_or(int v) {
     for (int o = L / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(FULLMASK, v, o, L);
     return v;
 }
+// any-over-CTA vote.  The barrier reduction returns the same value to every thread, but the compiler does not treat it as
+// warp-uniform: a loop that exits on it would count as divergent and every shuffle inside would be compiled with a
+// reconvergence sequence.  Passing it through a warp vote makes the uniformity visible.
+__device__ __forceinline__ int cta_or(int pred) { return __any_sync(FULLMASK, __syncthreads_or(pred)); }
 template <int L> constexpr int ilog2() { return L <= 1 ? 0 : 1 + ilog2<L / 2>(); }
 
 // |x| as the high word of the double: monotone in |x| for integer compares; NaN and inf sort above every finite value
@@ -377,6 +391,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
         valid = item < A.n_items;
         b = A.ids[valid ? item : A.n_items - 1];
     }
+    const bool queued = !GROUPED && A.queue != nullptr;
     const int Nt = a.Nt, NXT = a.Nx_t1, NXL = a.Nx_l1;
     const bool surf = a.flags & SFDTD_SURFACE_INTEGRAL;
     const bool save_state = a.flags & SFDTD_SAVE_STATE;
@@ -418,19 +433,62 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
     // transverse state rows n-1 / n-2 (in S, guards: 2 each side) and longitudinal arrays (in Lb, guard at [-1]); offsets swap
     int u1o = O_UA, u2o = O_UB;
     int z1o = 1, z2o = WLp + 1;
-    const int zao = 2 * WLp + 1, zbo = 3 * WLp + 1, rlo = 4 * WLp + 1, po = 5 * WLp + 1, zpo = 6 * WLp + 1;
+    const int zao = 2 * WLp + 1, zbo = 3 * WLp + 1, rlo = 4 * WLp + 1, zpo = 5 * WLp + 1;
     if (A.need_xax) {
         for (int i = tid; i < NXT; i += blockDim.x) xaxs[i] = a.xax[i];
         __syncthreads();
     }
+
+    // Work queue (independent mode): the grid is sized to what is resident at once and every warp pulls one set of 32/L strings
+    // after the other (hardest first), so that the load balances at warp granularity instead of in waves of whole CTAs.
+    // time slice of the current work item; kept in shared memory (n_lo, n_hi, set, slice index), not in registers
+    volatile int *const qst = (volatile int *)(cst + 6);
+    if (ln == 0) { qst[0] = A.n_lo; qst[1] = A.n_hi; qst[2] = 0; qst[3] = 0; }
+    __syncwarp();
+    int n_lo = A.n_lo, n_hi = A.n_hi;                                 // warp-uniform (kernel parameters or derived from the popped item)
+    for (bool q_first = true;; q_first = false) {
+    if (queued) {
+        // Items: first the A.q_full hardest sets, each for the whole call (longest first); then the remaining sets in time slices,
+        // slice-major (every set of that tail group advances through slice s before any starts slice s + 1, so the predecessor
+        // of a popped item was popped a whole group earlier and is normally long finished).  The slices keep the idle tail at
+        // the end of the bucket at a fraction of a slice instead of a fraction of a whole string.
+        int k = 0;
+        if ((tid & 31) == 0) k = atomicAdd(A.queue, 1);
+        k = __shfl_sync(FULLMASK, k, 0);
+        const int n_sets = (A.n_items + 32 / L - 1) / (32 / L), n_tail = n_sets - A.q_full;
+        int set = k, sidx = 0, lo = 2, hi = Nt;
+        if (k >= A.q_full) {
+            const int j = k - A.q_full;
+            if (n_tail <= 0 || j >= n_tail * A.q_nslices) break;
+            sidx = j / n_tail; set = A.q_full + (j - sidx * n_tail);
+            lo = 2 + sidx * A.q_slice; hi = min(Nt, lo + A.q_slice);
+        }
+        const int item = set * (32 / L) + (tid & 31) / L;
+        valid = item < A.n_items;
+        b = A.ids[valid ? item : A.n_items - 1];
+        status = 0; u1o = O_UA; u2o = O_UB; z1o = 1; z2o = WLp + 1;
+        __syncwarp();
+        if (ln == 0) { qst[0] = lo; qst[1] = hi; qst[2] = set; qst[3] = sidx; }
+        n_lo = lo; n_hi = hi;
+        if (sidx > 0) {
+            // every lane polls the same word and the exit is a warp vote: the loop is convergent by construction
+            for (;;) {
+                int v;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(A.done + set) : "memory");
+                if (!__any_sync(FULLMASK, v < sidx)) break;
+                __nanosleep(200);
+            }
+        }
+        __syncwarp();
+    } else if (!q_first) break;
 
     // ---- per-string constants ----
     const bool bowm = a.bow_mask[b] != 0, hamm = a.hammer_mask[b] != 0;
     const bool forced = bowm || hamm;
     bool group_has_hammer = false, group_has_bow = false;
     if (GROUPED) {
-        group_has_hammer = __syncthreads_or(valid && hamm);
-        group_has_bow = __syncthreads_or(valid && bowm);
+        group_has_hammer = cta_or(valid && hamm);
+        group_has_bow = cta_or(valid && bowm);
     }
     // CTA-uniform compute switches (they guard shuffles and barriers); per-string output switches
     const bool do_bow = group_has_bow || !skip_aux, do_ham = group_has_hammer || !skip_aux;
@@ -452,7 +510,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
         for (int j = ln; j < WLp; j += L) { LW[2 * j] = 0.0; LW[2 * j + 1] = 0.0; LI[j] = 0; }
         __syncwarp();
         // rows n_lo-2, n_lo-1: from the (B,Nt,Nx) history with SAVE_STATE, else from the compact (B,2,Nx) carry buffer
-        const int64_t row0 = save_state ? (int64_t)(A.n_lo - 2) : 0;
+        const int64_t row0 = save_state ? (int64_t)(qst[0] - 2) : 0;
         const double *su = (const double *)a.state_u.ptr + (int64_t)b * a.state_u.bs + row0 * a.state_u.ts;
 #pragma unroll
         for (int r = 0; r < ET; r++) {
@@ -467,7 +525,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
         }
     }
     double uH1 = 0.0, uH2 = 0.0;
-    if (Nt > 2) { uH2 = ldx(a.u_H, b, A.n_lo - 2); uH1 = ldx(a.u_H, b, A.n_lo - 1); }
+    if (Nt > 2) { const int n_lo = qst[0]; uH2 = ldx(a.u_H, b, n_lo - 2); uH1 = ldx(a.u_H, b, n_lo - 1); }
     uint32_t cnt_outer = 0, cnt_sweeps = 0, cnt_ham = 0, cnt_steps = 0;
     // cached interpolation rows of Int_tl for this lane's transverse rows (rebuilt when a grid size changes):
     // indices are stored +1 so that 0 addresses the zero guard (rows beyond N_t)
@@ -476,10 +534,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
     for (int r = 0; r < ET; r++) { tix[r] = 0; twb[r] = 0.f; }
     int curNt = -1, curNl = -1, ext1 = WLa, ext2 = WLa;               // ext: rows of Z1 / Z2 that may be non-zero
     float rho_h = 0.5f;                                               // contraction-rate history of the block iteration
+    int s_prev = 0;                                                   // sweeps the first solve of the previous step took (warp-uniform)
     __syncwarp();
 
-    const int n_hi = A.n_hi;
-    for (int n0 = A.n_lo; n0 < n_hi; n0 += TB) {
+    for (int n0 = n_lo; n0 < n_hi; n0 += TB) {
         // ================= scalar table for steps n0 .. n0+TB-1 (one step per lane) =================
         {
             const double kappa_rel = lds(a.kappa, b), alpha = lds(a.alpha, b);
@@ -735,8 +793,14 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 float e_prev = 0.f, isu = 0.f;
                 int zco = first ? zao : zfo;
                 const int keep_l = tabi[jj * NI + I_KEEPL];
+                // The first solve of a step needs about as many sweeps as the first solve of the previous step did (s_prev,
+                // warp-uniform): sweeps 1 .. s_prev-2 run without the stopping test and its bookkeeping (change norms, warp
+                // reductions); the test starts one sweep early so that the contraction rate is still measured.
+                const int s_skip = first ? s_prev - 2 : 0;
+                bool have_su = false, prev_chk = false;
                 do {
                     const int zno = (zco == zao) ? zbo : zao;
+                    const bool chk = sweeps >= s_skip;                              // warp-uniform
                     double d[ET];
                     {
                         double y[ET];
@@ -763,28 +827,33 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     // re-iterating a diverging string would move it and keep the group's fixed-point loop spinning)
                     const bool upd = !GROUPED || need;
                     unsigned du = 0u, su = 0u;
+                    float e = 0.f;
+                    bool dead = false;
+                    if (chk) {
 #pragma unroll
-                    for (int r = 0; r < ET; r++) {
-                        du = max(du, hi_abs(d[r] - xs[r]));
-                        if (sweeps == 0) su = max(su, hi_abs(d[r]));
-                        if (upd) xs[r] = d[r];
+                        for (int r = 0; r < ET; r++) {
+                            du = max(du, hi_abs(d[r] - xs[r]));
+                            if (!have_su) su = max(su, hi_abs(d[r]));
+                        }
                     }
+#pragma unroll
+                    for (int r = 0; r < ET; r++) if (upd) xs[r] = d[r];
                     // q = mu (x_i - x_{i-1})  (the scale phi/h_t^2 and the 1/h_t of Dxb are folded into T_PHL)
                     double xl = shup<L>(xs[ET - 1], 1);
                     if (ln == 0) xl = 0.0;
 #pragma unroll
                     for (int r = 0; r < ET; r++) qs[PRL(r)] = mu[r] * (xs[r] - (r == 0 ? xl : xs[r - 1]));
                     __syncwarp();
-                    if (upd) for (int j = ln; j <= WLs; j += L) {
-                        const int li = LI[j];
-                        const double2 w = *(const double2 *)(LW + 2 * j);
-                        Lb[po + j] = w.x * qs[li & 0xffff] + w.y * qs[li >> 16];
-                    }
-                    __syncwarp();
+                    // P = Int_lt q is evaluated where it is used (rows j and j+1): one shared-memory round trip and one warp
+                    // barrier fewer per sweep than staging P
                     {
                         const double PHL = t[T_PHL], idA = t[T_IDA], eidA = t[T_EIDA];
                         if (upd) for (int j = ln; j < WLs; j += L) {
-                            double rhs = PHL * (Lb[po + j + 1] - Lb[po + j]);
+                            const int li0 = LI[j], li1 = LI[j + 1];
+                            const double2 w0 = *(const double2 *)(LW + 2 * j), w1 = *(const double2 *)(LW + 2 * j + 2);
+                            const double pj = w0.x * qs[li0 & 0xffff] + w0.y * qs[li0 >> 16];
+                            const double pj1 = w1.x * qs[li1 & 0xffff] + w1.y * qs[li1 >> 16];
+                            double rhs = PHL * (pj1 - pj);
                             if (j < keep_l) rhs -= Lb[rlo + j];
                             const double zr = (j + 1 < WLs) ? Lb[zco + j + 1] : 0.0;
                             Lb[zno + j] = rhs * idA - eidA * (Lb[zco + j - 1] + zr);
@@ -793,35 +862,43 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     __syncwarp();
                     if (upd) zco = zno;
                     sweeps++;
-                    bool ok;
-                    if (sweeps == 1) {
-                        const float suf = hi_to_float(red_maxu<L>(su));
-                        isu = __fdividef(1.0f, suf);                                // 1/0 = inf: (0 * inf) = NaN ends the sweeps below
-                        ok = !(suf < INFINITY);                                     // NaN / inf state: nothing left to converge
-                    } else {
-                        // relative change of the transverse block in this sweep; predicted error  e * rho / (1 - rho).
-                        // The longitudinal block is an affine image of the transverse one (z = A22^-1(-r_l - K_lt x), Jacobi
-                        // error contracts by 2e-5 per sweep), so it needs no criterion of its own.
-                        const float e = hi_to_float(red_maxu<L>(du)) * isu;
-                        float rho = 2.0f * rho_h;
-                        if (sweeps >= 3) {
-                            // measured contraction rate e / e_prev (e_prev = 0: the iteration had already converged)
-                            const float rr = __fdividef(e, fmaxf(e_prev, 1e-37f));
-                            const float rh = (rr > rho_h) ? rr : 0.5f * (rho_h + rr);
-                            rho_h = conv ? rho_h : rh;
-                            rho = 1.5f * rho_h;
+                    bool ok = false;
+                    if (chk) {
+                        if (!have_su) {
+                            const float suf = hi_to_float(red_maxu<L>(su));
+                            isu = __fdividef(1.0f, suf);                            // 1/0 = inf: (0 * inf) = NaN ends the sweeps below
+                            dead = !(suf < INFINITY);                               // NaN / inf state: nothing left to converge
+                            have_su = true;
                         }
-                        rho = fminf(rho, 0.9f);
-                        // e rho / (1 - rho) <= tol, without the division
-                        // (a warm-started re-solve of a later fixed-point pass starts from the previous pass's solution: its
-                        // very first change is already a meaningful error measure)
-                        ok = (sweeps >= ((keep_l > 0) ? 4 : (first ? 3 : 2))) && !(e * rho > GS_TOL * (1.0f - rho));
-                        ok = ok || !(e < INFINITY);
-                        e_prev = e;
-                        if (sweeps >= GS_CAP && !ok && !conv) { status |= SFDTD_ST_SOLVER_CAP; capped = true; ok = true; }
+                        if (sweeps > 1) e = hi_to_float(red_maxu<L>(du)) * isu;      // relative change of the transverse block in this sweep
+                        if (sweeps == 1) {
+                            ok = dead;
+                        } else {
+                            // predicted error  e * rho / (1 - rho).
+                            // The longitudinal block is an affine image of the transverse one (z = A22^-1(-r_l - K_lt x), Jacobi
+                            // error contracts by 2e-5 per sweep), so it needs no criterion of its own.
+                            float rho = 2.0f * rho_h;
+                            if (sweeps >= 3 && prev_chk) {
+                                // measured contraction rate e / e_prev (e_prev = 0: the iteration had already converged)
+                                const float rr = __fdividef(e, fmaxf(e_prev, 1e-37f));
+                                const float rh = (rr > rho_h) ? rr : 0.5f * (rho_h + rr);
+                                rho_h = conv ? rho_h : rh;
+                                rho = 1.5f * rho_h;
+                            }
+                            rho = fminf(rho, 0.9f);
+                            // e rho / (1 - rho) <= tol, without the division
+                            // (a warm-started re-solve of a later fixed-point pass starts from the previous pass's solution: its
+                            // very first change is already a meaningful error measure)
+                            ok = (sweeps >= ((keep_l > 0) ? 4 : (first ? 3 : 2))) && !(e * rho > GS_TOL * (1.0f - rho));
+                            ok = ok || !(e < INFINITY) || dead;
+                            e_prev = e;
+                            if (sweeps >= GS_CAP && !ok && !conv) { status |= SFDTD_ST_SOLVER_CAP; capped = true; ok = true; }
+                        }
                     }
+                    prev_chk = chk;
                     if (!conv) { cnt_sweeps += 1; conv = ok; }
-                } while (__any_sync(FULLMASK, !conv));
+                } while (sweeps < s_skip || __any_sync(FULLMASK, !conv));          // no vote while the test is off
+                if (first) s_prev = SFDTD_PREDICT_SWEEPS ? sweeps : 0;
                 zfo = zco;
             };
 
@@ -981,7 +1058,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                             eta_est = (uH - eps_u) * hm;
                             const int nc = fabs(eta - eta_est) > tol_t;
                             hit++;
-                            more = group_has_hammer ? __syncthreads_or(valid && nc) : nc;
+                            more = group_has_hammer ? cta_or(valid && nc) : __any_sync(FULLMASK, nc);
                             if (hit >= A.max_iter) { if (more) status |= SFDTD_ST_HAMMER_CAP; more = 0; }
                         } while (more);
                         cnt_ham += hit;
@@ -1032,7 +1109,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     // a string whose linear iteration diverges has no fixed point to wait for: it does not vote
                     const int not_conv = !capped && ((nc_t && !nan_u) || (nc_l && !nan_z));
                     iter++;
-                    int more = __syncthreads_or(valid && not_conv);
+                    int more = cta_or(valid && not_conv);
                     if (iter >= A.max_iter) { if (more) status |= SFDTD_ST_OUTER_CAP; more = 0; }
                     if (!more) break;
                 }
@@ -1144,11 +1221,11 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
             for (int j = ln; j < WLa; j += L) if (j < NXL) { sz[j] = Lb[z2o + j]; sz[a.state_z.ts + j] = Lb[z1o + j]; }
         }
         // u_H_out / u_H columns 0,1 (simulator.cpp:57 divides the whole tensor)
-        if (ln < 2 && ln < Nt && A.n_lo == 2) {
+        if (ln < 2 && ln < Nt && qst[0] == 2) {
             ((double *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)ln * a.u_H_out.ts] = ldx(a.u_H, b, ln) * A.ik;
         }
         if (ln == 0) {
-            if (Nt > 2 && n_hi == Nt) {
+            if (Nt > 2 && qst[1] == Nt) {
                 // loss parameters of the last step (string.cpp:119-120)
                 const Derived d = derive(ldx(a.f0, b, Nt - 1), lds(a.kappa, b), lds(a.alpha, b), A);
                 const double *T60 = (const double *)a.T60.ptr + (int64_t)b * a.T60.bs;
@@ -1173,6 +1250,16 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
             }
         }
     }
+    __syncwarp();
+    if (queued) {
+        // hand the state rows (and u_H) of this slice over to whichever warp runs the set's next slice
+        __threadfence();
+        __syncwarp();
+        // (every lane stores the same word: a store under a lane predicate at the loop's back edge makes the compiler treat
+        // the whole loop body as possibly diverged and wrap every shuffle in a reconvergence sequence)
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(A.done + qst[2]), "r"(qst[3] + 1) : "memory");
+    }
+    }   // work-queue loop
 }
 
 
@@ -1209,9 +1296,13 @@ struct Config { int L, ET, maxt; bool grouped; int tier; void (*kern)(const KArg
 const Config g_configs[] = {
     CFG_I(8, 4, 3, 0), CFG_I(8, 6, 2, 0), CFG_I(16, 4, 3, 0), CFG_I(16, 6, 2, 0), CFG_I(32, 4, 3, 0), CFG_I(32, 8, 1, 0),
     CFG_I(16, 4, 3, 2), CFG_I(32, 4, 3, 2), CFG_I(32, 8, 1, 2),
-    CFG_G(8, 4, 256), CFG_G(8, 6, 256), CFG_G(16, 4, 512), CFG_G(16, 6, 384), CFG_G(32, 4, 1024), CFG_G(32, 8, 128), CFG_G(32, 8, 512),
+    CFG_I(8, 4, 3, 3), CFG_I(16, 4, 3, 3), CFG_I(32, 4, 3, 3), CFG_I(32, 8, 1, 3),
+    CFG_G(8, 4, 256), CFG_G(8, 6, 256), CFG_G(16, 4, 384), CFG_G(16, 4, 512), CFG_G(16, 6, 384), CFG_G(32, 4, 1024), CFG_G(32, 8, 128), CFG_G(32, 8, 512),
 };
-constexpr int DEFAULT_TIER = 2;
+#ifndef SFDTD_DEFAULT_TIER
+#define SFDTD_DEFAULT_TIER 2
+#endif
+constexpr int DEFAULT_TIER = SFDTD_DEFAULT_TIER;
 constexpr int N_CONFIGS = sizeof(g_configs) / sizeof(g_configs[0]);
 
 // longitudinal allocation classes of the independent mode (rows incl. the two guards)
@@ -1315,7 +1406,10 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     int rc = SFDTD_OK, dev = 0;
     bool locked = false;
     const int n_groups = (a.B + a.group_size - 1) / a.group_size;
-    int32_t *d_max = nullptr, *d_ids = nullptr, *d_wtab = nullptr;
+    int32_t *d_max = nullptr, *d_ids = nullptr, *d_wtab = nullptr, *d_queue = nullptr, *d_done = nullptr;
+    int n_sms = 0;
+    size_t q_off = 0;
+    const bool use_queue = getenv("SFDTD_QUEUE") ? atoi(getenv("SFDTD_QUEUE")) != 0 : SFDTD_DEFAULT_QUEUE;
     float *d_est = nullptr;
     std::vector<float> h_est(a.B);
     std::vector<int32_t> h_max(2 * (size_t)a.B);
@@ -1328,7 +1422,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     std::vector<TimedBucket> timed;
     const bool verbose = getenv("SFDTD_VERBOSE") != nullptr;
     const bool skip_aux = a.flags & SFDTD_SKIP_AUX;
-    const int tier = getenv("SFDTD_TIER") ? std::min(2, std::max(0, atoi(getenv("SFDTD_TIER")))) : DEFAULT_TIER;
+    const int tier = getenv("SFDTD_TIER") ? std::min(3, std::max(0, atoi(getenv("SFDTD_TIER")))) : DEFAULT_TIER;
 
     KArgs K;
     memset(&K, 0, sizeof K);
@@ -1429,6 +1523,13 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
             g_side_streams.push_back(s); g_side_events.push_back(e);
         }
         if (!g_fork_event) CK(cudaEventCreateWithFlags(&g_fork_event, cudaEventDisableTiming));
+        if (use_queue) {
+            // counters: one per bucket, then one "slices done" word per set of strings (<= one per string)
+            CK(scratch_get(dev, 4, sizeof(int32_t) * (nb + (size_t)a.B + nb), (void **)&d_queue));
+            CK(cudaMemsetAsync(d_queue, 0, sizeof(int32_t) * (nb + (size_t)a.B + nb), stream));
+            d_done = d_queue + nb;
+            CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+        }
         CK(cudaEventRecord(g_fork_event, stream));
         // launch order: smallest buckets first.  Every CTA lives for the whole time loop, so a small bucket started late
         // would trail the bulk by a full CTA lifetime on a nearly empty GPU; started first it overlaps with the bulk.
@@ -1489,6 +1590,27 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
             // one shared-memory carve-out for every bucket kernel, so that CTAs of different buckets can share an SM
             CK(cudaFuncSetAttribute(cf.kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             K.ids = d_ids + off; K.n_items = n_items; K.WLp = WLp; K.need_xax = need_xax ? 1 : 0;
+            K.queue = nullptr;
+            if (use_queue && !cf.grouped && n_slices == 1) {
+                // persistent grid: what is resident at once; the warps pull their string sets from the bucket's counter
+                int per_sm = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf.kern, threads, sm));
+                const int spw = 32 / cf.L, n_sets = (n_items + spw - 1) / spw, wpc = threads / 32;
+                const int resident = std::max(1, per_sm) * n_sms;
+                // tail group: the sets that would run in the last round of the resident warps, in SFDTD_QSLICES time slices
+                // (default 8); a bucket with fewer than two rounds of sets is not sliced (it ends long before the bulk does)
+                const int rw = resident * wpc;
+                const int want = getenv("SFDTD_QSLICES") ? atoi(getenv("SFDTD_QSLICES")) : 8;
+                int n_sl = std::max(1, std::min(want, (a.Nt - 2) / 512));
+                const int q_slice = ((a.Nt - 2 + n_sl - 1) / n_sl + TBS - 1) / TBS * TBS;
+                n_sl = (a.Nt - 2 + q_slice - 1) / q_slice;
+                const double tail_rounds = getenv("SFDTD_QTAIL") ? atof(getenv("SFDTD_QTAIL")) : 1.0;
+                const int n_tail = (n_sl > 1 && n_sets >= 2 * rw) ? std::min(n_sets, (int)(tail_rounds * rw)) : 0;
+                grid = std::min(std::min(grid, resident), (n_sets + wpc - 1) / wpc);
+                K.q_slice = q_slice; K.q_nslices = n_sl; K.q_full = n_sets - n_tail;
+                K.queue = d_queue + bi; K.done = d_done + q_off;
+                q_off += n_sets;
+            }
             cudaStream_t s = (nb > 1) ? g_side_streams[bi] : stream;
             if (nb > 1 && si == 0) CK(cudaStreamWaitEvent(s, g_fork_event, 0));
             if (verbose && si == 0) {
