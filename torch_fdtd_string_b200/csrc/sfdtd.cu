@@ -351,14 +351,24 @@ template <int L, int ET> __device__ __forceinline__ double fetch_row(const doubl
 
 
 // shared-memory doubles of the fixed part of a string slot, and of its longitudinal part (W rows incl. guards, W even)
-__host__ __device__ inline int slot_fixed_doubles(int L, int ET, bool grouped) {
-    const int LE = L * ET;
-    int n = TBS * (grouped ? NV_G : NV_I) + TBS * NI / 2 + TBS * NOUT + NCONST + (LE + L + 2) + 2 * (LE + L + 6) + (grouped ? LE + L : 0);
+// Two 8-lane strings share a 16-lane shared-memory wavefront: their slots are spaced by 8 (mod 16) doubles, which puts the
+// blocked row accesses (lane stride ET+1 doubles, ET = 4 or 6) and the consecutive longitudinal accesses of the two strings
+// into disjoint banks.
+__host__ __device__ inline int slot_spacing(int n, int L) {
     n = (n + 1) & ~1;                 // 16-byte aligned slots (int4 / double2 loads)
-    if ((n & 15) == 0) n += 2;        // ... that do not start in the same bank
+    if (L <= 8) n += (24 - (n & 15)) & 15;      // == 8 (mod 16)
+    else if ((n & 15) == 0) n += 2;   // one string per half-warp: the slots only should not start in the same bank
     return n;
 }
-__host__ __device__ inline int slot_long_doubles(int W, bool grouped) { return ((grouped ? NLA_G : NLA_I) * W + 2 * W + (W + 1) / 2 + 1) & ~1; }
+__host__ __device__ inline int slot_fixed_doubles(int L, int ET, bool grouped) {
+    const int LE = L * ET;
+    const int n = TBS * (grouped ? NV_G : NV_I) + TBS * NI / 2 + TBS * NOUT + NCONST + (LE + L + 2) + 2 * (LE + L + 6) + (grouped ? LE + L : 0);
+    return slot_spacing(n, L);
+}
+__host__ __device__ inline int slot_long_doubles(int W, bool grouped, int L) {
+    const int n = ((grouped ? NLA_G : NLA_I) * W + 2 * W + (W + 1) / 2 + 1) & ~1;
+    return L <= 8 ? slot_spacing(n, L) : n;
+}
 __host__ __device__ inline int long_rows(int maxNl) { return (maxNl + 1 + WL_MARGIN + 2 + 1) & ~1; }   // + 2 guards, even
 
 // ======================================================================================================
@@ -410,7 +420,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
         // per-string longitudinal allocation (sized by the string's own largest N_l), offsets by a prefix sum
         int *ioffs = (int *)Lb;                                       // [nslots + 2]
         WLp = long_rows(A.maxNl[b]);
-        if (ln == 0) ioffs[sl + 1] = slot_long_doubles(WLp, true);
+        if (ln == 0) ioffs[sl + 1] = slot_long_doubles(WLp, true, L);
         __syncthreads();
         if (tid == 0) { ioffs[0] = ((nslots + 2) / 2 + 1) & ~1; for (int q = 0; q < nslots; q++) ioffs[q + 1] += ioffs[q]; }
         __syncthreads();
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
         Lb += off;
     } else {
         WLp = A.WLp;
-        Lb += (size_t)sl * slot_long_doubles(WLp, false);
+        Lb += (size_t)sl * slot_long_doubles(WLp, false, L);
     }
     const int WLa = WLp - 2;                                          // usable longitudinal rows (guards at -1 and WLa)
     double *const tab = S;                                            // [TB][NV]
@@ -1316,7 +1326,7 @@ size_t xax_doubles(int NXT, bool need_xax) { return need_xax ? (size_t)((NXT + 3
 
 // independent mode: nslots strings with WLp longitudinal rows each
 size_t smem_bytes_indep(const Config &c, int nslots, int NXT, int WLp, bool need_xax) {
-    const size_t dbl = xax_doubles(NXT, need_xax) + (size_t)nslots * (slot_fixed_doubles(c.L, c.ET, false) + slot_long_doubles(WLp, false));
+    const size_t dbl = xax_doubles(NXT, need_xax) + (size_t)nslots * (slot_fixed_doubles(c.L, c.ET, false) + slot_long_doubles(WLp, false, c.L));
     return dbl * sizeof(double) + 16;
 }
 
@@ -1496,7 +1506,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
             const Config &cf = g_configs[pick];
             const int threads = (a.group_size * cf.L + 31) / 32 * 32, nslots = threads / cf.L;
             size_t dbl = xax_doubles(a.Nx_t1, true) + (size_t)nslots * slot_fixed_doubles(cf.L, cf.ET, true) + (size_t)(nslots + 2) / 2 + 2;
-            for (int s = 0; s < nslots; s++) dbl += slot_long_doubles(long_rows(h_max[a.B + g0 + std::min(s, G - 1)]), true);
+            for (int s = 0; s < nslots; s++) dbl += slot_long_doubles(long_rows(h_max[a.B + g0 + std::min(s, G - 1)]), true, cf.L);
             Bucket &bk = buckets[{pick, 0}];
             bk.ids.push_back(g);
             bk.smem = std::max(bk.smem, dbl * sizeof(double) + 16);
