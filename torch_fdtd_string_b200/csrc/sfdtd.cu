@@ -1615,7 +1615,9 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
                 const int q_slice = ((a.Nt - 2 + n_sl - 1) / n_sl + TBS - 1) / TBS * TBS;
                 n_sl = (a.Nt - 2 + q_slice - 1) / q_slice;
                 const double tail_rounds = getenv("SFDTD_QTAIL") ? atof(getenv("SFDTD_QTAIL")) : 1.0;
-                const int n_tail = (n_sl > 1 && n_sets >= 2 * rw) ? std::min(n_sets, (int)(tail_rounds * rw)) : 0;
+                // (SFDTD_QMIN: rounds of sets below which a bucket is not sliced; 0 forces the sliced path for the tests)
+                const double min_rounds = getenv("SFDTD_QMIN") ? atof(getenv("SFDTD_QMIN")) : 2.0;
+                const int n_tail = (n_sl > 1 && n_sets >= min_rounds * rw) ? std::max(0, std::min(n_sets, (int)(tail_rounds * rw))) : 0;
                 grid = std::min(std::min(grid, resident), (n_sets + wpc - 1) / wpc);
                 K.q_slice = q_slice; K.q_nslices = n_sl; K.q_full = n_sets - n_tail;
                 K.queue = d_queue + bi; K.done = d_done + q_off;
