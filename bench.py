@@ -34,9 +34,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--strings", type=int, default=148 * GROUP * 4, help="strings per GPU (multiple of 24); BASELINE configs[4] sweeps 1k..1M")
+    ap.add_argument("--strings", type=int, default=148 * GROUP * 8, help="strings per GPU (multiple of 24); BASELINE configs[4] sweeps 1k..1M; the default (28416) needs 133 GB of HBM at 1 s")
     ap.add_argument("--length", type=float, default=1.0, help="seconds of audio per string")
     ap.add_argument("--excitation", default="pluck")
+    ap.add_argument("--group", type=int, default=GROUP, help="strings per reference batch (task.batch_size); diagnostics only")
     ap.add_argument("--skip-aux", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -138,28 +139,38 @@ def algorithmic_work(p, ctl, counters, group):
     import torch
     k = float(np.float32(p["k"])); th = float(np.float32(p["theta_t"])); lam = float(np.float32(p["lambda_c"]))
     tt1 = float(np.float32(2 * np.float32(th) - 1)); tt2 = float(np.float32(2 * np.float32(tt1)))
-    f0 = ctl["f0"][:, 2:]
-    B = f0.size(0)
-    gamma = 2 * f0
-    K = gamma * p["kappa"].view(-1, 1)
-    h1 = lam * ((gamma ** 2 * k ** 2 + (gamma ** 4 * k ** 4 + 16 * K ** 2 * k ** 2 * tt1).sqrt()) / tt2).sqrt()
-    Nt_ = (1 / h1).floor()
-    Nl_ = (1 / (lam * gamma * p["alpha"].view(-1, 1) * k)).floor()
-    gpu_updates = float((Nt_ + 1 + Nl_ + 1).sum())
-    G = B // group
-    Wt = (Nt_.view(G, group, -1).max(dim=1).values + 1)
-    Wl = (Nl_.view(G, group, -1).max(dim=1).values + 1)
-    S = (1 + p["bow_mask"].double() + p["hammer_mask"].double()).view(G, group, 1)
-    I = (counters[:, 0].double() / counters[:, 3].clamp(min=1).double()).view(G, group, 1)
-    Wt_ = Wt.unsqueeze(1); Wl_ = Wl.unsqueeze(1)
-    F = (60 * Wt_ + 30 * Wl_) + S * (110 * Wt_ + 74 * Wl_) + I * (4 * (Wt_ + Wl_) + 50)
+    f0_all = ctl["f0"][:, 2:]
+    B = f0_all.size(0)
+    F_sum = gpu_updates = Wt_sum = Wl_sum = 0.0
+    gpc = max(1, 4096 // group)                                  # groups per chunk: the temporaries are (strings, Nt) sized
+    for g0 in range(0, B // group, gpc):
+        sl = slice(g0 * group, min(B, (g0 + gpc) * group))
+        f0 = f0_all[sl]
+        G = f0.size(0) // group
+        gamma = 2 * f0
+        K = gamma * p["kappa"][sl].view(-1, 1)
+        h1 = lam * ((gamma ** 2 * k ** 2 + (gamma ** 4 * k ** 4 + 16 * K ** 2 * k ** 2 * tt1).sqrt()) / tt2).sqrt()
+        Nt_ = (1 / h1).floor()
+        Nl_ = (1 / (lam * gamma * p["alpha"][sl].view(-1, 1) * k)).floor()
+        gpu_updates += float((Nt_ + 1 + Nl_ + 1).sum())
+        Wt = (Nt_.view(G, group, -1).max(dim=1).values + 1)
+        Wl = (Nl_.view(G, group, -1).max(dim=1).values + 1)
+        S = (1 + p["bow_mask"][sl].double() + p["hammer_mask"][sl].double()).view(G, group, 1)
+        I = (counters[sl, 0].double() / counters[sl, 3].clamp(min=1).double()).view(G, group, 1)
+        Wt_ = Wt.unsqueeze(1); Wl_ = Wl.unsqueeze(1)
+        F = (60 * Wt_ + 30 * Wl_) + S * (110 * Wt_ + 74 * Wl_) + I * (4 * (Wt_ + Wl_) + 50)
+        F_sum += float(F.sum()); Wt_sum += float(Wt.sum()); Wl_sum += float(Wl.sum())
+        del gamma, K, h1, Nt_, Nl_, F
+    n_wt = (B // group) * f0_all.size(1)
     # bytes: 6 control reads + 5 output writes per string-step (fp64) + initial rows
-    bytes_ = B * f0.size(1) * 11 * 8 + B * 2 * (p["Nx_t1"] + p["Nx_l1"]) * 8
-    return float(F.sum()), gpu_updates, float(bytes_), float(Wt.mean()), float(Wl.mean())
+    bytes_ = B * f0_all.size(1) * 11 * 8 + B * 2 * (p["Nx_t1"] + p["Nx_l1"]) * 8
+    return F_sum, gpu_updates, float(bytes_), Wt_sum / n_wt, Wl_sum / n_wt
 
 
 def main():
+    global GROUP
     a = parse()
+    GROUP = a.group
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if a.impl == "reference":
@@ -327,6 +338,7 @@ def main():
         "mean_operator_widths": {"W_t": Wt_mean, "W_l": Wl_mean},
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clk, "step_ms": [round(x, 2) for x in step_ms],
+        "peak_device_memory_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
         "health": {"status_bits": status, "nan_strings": nan_strings,
                    "mean_outer_iters": float(counters[:, 0].sum()) / max(1.0, float(counters[:, 3].sum())),
                    "mean_sweeps_per_step": float(counters[:, 1].sum()) / max(1.0, float(counters[:, 3].sum())),

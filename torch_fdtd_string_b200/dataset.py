@@ -71,7 +71,7 @@ def save_simulation_data(directory, excitation_type, simulation_dict, string_dic
 
 def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000, length=1.0, seed=1234,
              precision="double", normalize_output=True, skip_silence=True, silence_threshold=-23.0, save=True,
-             randomize_name=False, batches_per_call=64, rank=0, world_size=1, device=None, surface_integral=True,
+             randomize_name=False, batches_per_call=296, rank=0, world_size=1, device=None, surface_integral=True,
              sampler_cfg=None, time_log=False):
     """Generates ``num_samples // batch_size`` reference batches (reference run.py:109) and writes the kept strings.
     Returns dict(strings, written, nan, silent, seconds_stepper)."""

@@ -169,12 +169,27 @@ def f0_min_over_time(p, Nt, k, block=4096):
     return lo
 
 
-def expand_controls(p, device, n_run=None):
+def expand_controls(p, device, n_run=None, chunk=4096):
     """compact description (already on `device`) -> dict of (B,n_run) float64 control curves on the device:
-    the first `n_run` samples (default: all `Nt`) of the curves defined over the full length `Nt`."""
+    the first `n_run` samples (default: all `Nt`) of the curves defined over the full length `Nt`.  Evaluated `chunk`
+    strings at a time into preallocated outputs, so that the temporaries stay small next to the curves themselves."""
+    Nt, B = p["Nt"], p["B"]
+    n_run = Nt if n_run is None else int(n_run)
+    out = {k: torch.empty(B, n_run, dtype=torch.float64, device=device) for k in ("f0", "x_b", "v_b", "F_b", "u_H")}
+    for s0 in range(0, B, chunk):
+        sl = slice(s0, min(B, s0 + chunk))
+        q = {k: (v[sl] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.size(0) == B else v) for k, v in p.items()}
+        q["B"] = sl.stop - sl.start
+        c = _expand_chunk(q, device, n_run)
+        for k in out:
+            out[k][sl] = c[k]
+    out["wid"] = p["wid"].view(-1, 1).expand(B, n_run)                                 # time stride 0
+    return out
+
+
+def _expand_chunk(p, device, n_run):
     Nt, k, sr = p["Nt"], p["k"], p["sr"]
     B = p["B"]
-    n_run = Nt if n_run is None else int(n_run)
     t = torch.arange(1, n_run + 1, dtype=torch.float64, device=device).view(1, -1)
     ramp = (t - 1) / max(Nt - 1, 1)
     lin = lambda a, b: a.view(-1, 1) + (b - a).view(-1, 1) * ramp
@@ -186,11 +201,10 @@ def expand_controls(p, device, n_run=None):
     off = (Nt - (sr * p["pulloff"]).floor()).view(-1, 1)
     w = torch.tanh((Nt - (t - 1) - off).clamp(min=0) / sr * 100)
     F_b = torch.where(p["pulloff"].view(-1, 1) > 0, F_b * w, F_b)
-    wid = p["wid"].view(-1, 1).expand(B, n_run)                                       # time stride 0
     u_H = torch.zeros(B, n_run, dtype=torch.float64, device=device)                      # simulator.py:573-578
     u_H[:, :2] = -1e-3
     u_H[:, 1] += k * p["v_H"]
-    return dict(f0=f0, x_b=x_b, v_b=v_b, F_b=F_b, wid=wid, u_H=u_H)
+    return dict(f0=f0, x_b=x_b, v_b=v_b, F_b=F_b, u_H=u_H)
 
 
 def fletcher_w0(kappa):
