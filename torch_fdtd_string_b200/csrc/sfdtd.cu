@@ -65,7 +65,11 @@ constexpr int GS_CAP = 60;          // cap on block Gauss-Seidel sweeps per solv
 constexpr float GS_TOL = 1e-13f;    // predicted relative max-norm error of the transverse block that ends the sweeps
 constexpr int NLA_I = 5;            // longitudinal arrays per string, independent mode: Z1 Z2 ZA ZB RL
 constexpr int NLA_G = 6;            // grouped mode: + ZP (previous fixed-point iterate)
-constexpr int TBS = 8;              // time steps per scalar-table block
+// time steps per scalar-table block.  Independent mode: 16 = one step per lane of a 16-lane string, so that the table code
+// (divisions, square roots) runs with every lane busy and the control prefetch / output flush move 128-byte rows (+6...8 %
+// over 8); grouped mode: 8, its CTAs are at the shared-memory limit.
+constexpr int TBS_I = 16, TBS_G = 8;
+constexpr int TBS_MAX = TBS_I > TBS_G ? TBS_I : TBS_G;
 #ifndef SFDTD_PREDICT_SWEEPS
 #define SFDTD_PREDICT_SWEEPS 1
 #endif
@@ -289,7 +293,7 @@ template <int L, int ET> struct TriSolver {
 #pragma unroll
         for (int r = M - 2; r >= 0; r--) Y[r] = fma(-cp[r], Y[r + 1], Y[r]);
         double Yn0 = shdn<L>(Y[0], 1);
-        if (ln == L - 1) Yn0 = 0.0;
+        // (no boundary select: ce = 0 in the last lane, whose last row has no right neighbour; the shuffle returns its own Y[0])
         double D = d[ET - 1] - ae * Y[M - 1] - ce * Yn0;
 #pragma unroll
         for (int lv = 0; lv < LV; lv++) {
@@ -299,7 +303,7 @@ template <int L, int ET> struct TriSolver {
         }
         const double xe = D * invB;
         double p = shup<L>(xe, 1);
-        if (ln == 0) p = 0.0;
+        // (no boundary select: the left spike V is 0 in lane 0, whose first row has no left neighbour)
 #pragma unroll
         for (int r = 0; r < M; r++) d[r] = Y[r] - V[r] * p - W[r] * xe;
         d[ET - 1] = xe;
@@ -362,6 +366,7 @@ __host__ __device__ inline int slot_spacing(int n, int L) {
 }
 __host__ __device__ inline int slot_fixed_doubles(int L, int ET, bool grouped) {
     const int LE = L * ET;
+    const int TBS = grouped ? TBS_G : TBS_I;
     const int n = TBS * (grouped ? NV_G : NV_I) + TBS * NI / 2 + TBS * NOUT + NCONST + (LE + L + 2) + 2 * (LE + L + 6) + (grouped ? LE + L : 0);
     return slot_spacing(n, L);
 }
@@ -374,7 +379,7 @@ __host__ __device__ inline int long_rows(int maxNl) { return (maxNl + 1 + WL_MAR
 // ======================================================================================================
 template <int L, int ET, bool GROUPED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_constant__ KArgs A) {
-    constexpr int TB = TBS;
+    constexpr int TB = GROUPED ? TBS_G : TBS_I;
     constexpr int LE = L * ET;
     constexpr int NLA = GROUPED ? NLA_G : NLA_I;
     constexpr int NV = GROUPED ? NV_G : NV_I;
@@ -1612,7 +1617,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
                 const int rw = resident * wpc;
                 const int want = getenv("SFDTD_QSLICES") ? atoi(getenv("SFDTD_QSLICES")) : 8;
                 int n_sl = std::max(1, std::min(want, (a.Nt - 2) / 512));
-                const int q_slice = ((a.Nt - 2 + n_sl - 1) / n_sl + TBS - 1) / TBS * TBS;
+                const int q_slice = ((a.Nt - 2 + n_sl - 1) / n_sl + TBS_MAX - 1) / TBS_MAX * TBS_MAX;
                 n_sl = (a.Nt - 2 + q_slice - 1) / q_slice;
                 const double tail_rounds = getenv("SFDTD_QTAIL") ? atof(getenv("SFDTD_QTAIL")) : 1.0;
                 // (SFDTD_QMIN: rounds of sets below which a bucket is not sliced; 0 forces the sliced path for the tests)
