@@ -103,7 +103,7 @@ def reference_arm(a, rank):
     Nt_s = a.ref_nt
     cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--B", str(GROUP), "--nt", str(Nt_s),
            "--steps", str(a.steps), "--warmup", str(a.warmup), "--excitation", a.excitation]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=3000)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=3000, env=host_thread_env())
     line = [l for l in out.stdout.splitlines() if l.startswith("{")]
     if not line:
         print(json.dumps({"impl": "reference", "unavailable": (out.stderr.strip().splitlines() or ["no output"])[-1][:200]}))
@@ -122,6 +122,15 @@ def reference_arm(a, rank):
         "e2e": {"value": val, "unit": "string-seconds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def host_thread_env():
+    """environment of the CPU reference: every host core (torchrun exports OMP_NUM_THREADS=1 to its ranks, which would
+    make the reference single-threaded exactly when it is launched like the GPU arm)"""
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        env.pop(k, None)
+    return env
 
 
 def workload_config(a, strings):
@@ -320,7 +329,7 @@ def main():
         try:
             o = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--B", str(GROUP), "--nt", "62",
                                 "--steps", "1", "--warmup", "0", "--excitation", a.excitation],
-                               capture_output=True, text=True, timeout=1200)
+                               capture_output=True, text=True, timeout=1200, env=host_thread_env())
             r = json.loads([l for l in o.stdout.splitlines() if l.startswith("{")][-1])
             t = r["sec_per_call"][0]
             cpu = {"value": GROUP * 60 / SR / t, "unit": "string-seconds/s", "cores": r["cores"], "kind": r["kind"],

@@ -73,6 +73,12 @@ constexpr int TBS_MAX = TBS_I > TBS_G ? TBS_I : TBS_G;
 #ifndef SFDTD_PREDICT_SWEEPS
 #define SFDTD_PREDICT_SWEEPS 1
 #endif
+#ifndef SFDTD_DEFAULT_WLMIN
+#define SFDTD_DEFAULT_WLMIN 16      // smallest longitudinal allocation class (rows incl. guards)
+#endif
+#ifndef SFDTD_DEFAULT_LANE_DIV
+#define SFDTD_DEFAULT_LANE_DIV 4
+#endif
 #ifndef SFDTD_DEFAULT_QUEUE
 #define SFDTD_DEFAULT_QUEUE 1
 #endif
@@ -1321,8 +1327,8 @@ constexpr int DEFAULT_TIER = SFDTD_DEFAULT_TIER;
 constexpr int N_CONFIGS = sizeof(g_configs) / sizeof(g_configs[0]);
 
 // longitudinal allocation classes of the independent mode (rows incl. the two guards)
-int wl_class(int rows) {
-    int c = 16;
+int wl_class(int rows, int c_min = 16) {
+    int c = c_min;
     while (c < rows) c *= 2;
     return c;
 }
@@ -1424,6 +1430,11 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     int32_t *d_max = nullptr, *d_ids = nullptr, *d_wtab = nullptr, *d_queue = nullptr, *d_done = nullptr;
     int n_sms = 0;
     size_t q_off = 0;
+    // smallest longitudinal allocation class: a coarser one merges buckets (one work queue balances more strings) for more
+    // shared memory per string
+    const int wl_min = getenv("SFDTD_WLMIN") ? std::max(16, atoi(getenv("SFDTD_WLMIN"))) : SFDTD_DEFAULT_WLMIN;
+    // longitudinal rows per lane that still count as a short loop (lanes >= allocation class / lane_div)
+    const int lane_div = getenv("SFDTD_LANE_DIV") ? std::max(1, atoi(getenv("SFDTD_LANE_DIV"))) : SFDTD_DEFAULT_LANE_DIV;
     const bool use_queue = getenv("SFDTD_QUEUE") ? atoi(getenv("SFDTD_QUEUE")) != 0 : SFDTD_DEFAULT_QUEUE;
     float *d_est = nullptr;
     std::vector<float> h_est(a.B);
@@ -1482,8 +1493,8 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
             const int rows = std::min(Wt, h_max[g0 + s] + 3 + (h_bow[g0 + s] ? 8 : 0));
             if (!forced) {
                 // lanes: enough rows for the transverse block, and enough lanes that the longitudinal loops stay short
-                const int wlc = wl_class(long_rows(h_max[a.B + g0 + s]));
-                const int min_lanes = std::max(std::min(32, wlc / 4), getenv("SFDTD_MIN_LANES") ? atoi(getenv("SFDTD_MIN_LANES")) : 0);
+                const int wlc = wl_class(long_rows(h_max[a.B + g0 + s]));       // lanes follow the string's own size ...
+                const int min_lanes = std::max(std::min(32, wlc / lane_div), getenv("SFDTD_MIN_LANES") ? atoi(getenv("SFDTD_MIN_LANES")) : 0);
                 int pick = -1;
                 for (int c = 0; c < N_CONFIGS && pick < 0; c++)
                     if (!g_configs[c].grouped && g_configs[c].tier == tier && rows <= g_configs[c].L * g_configs[c].ET &&
@@ -1492,7 +1503,7 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
                     snprintf(g_err, sizeof g_err, "string %d: %d transverse rows are outside the built kernel set", g0 + s, rows);
                     rc = SFDTD_ERR_UNSUPPORTED; goto done;
                 }
-                buckets[{pick, wl_class(long_rows(h_max[a.B + g0 + s]))}].ids.push_back(g0 + s);
+                buckets[{pick, wl_class(long_rows(h_max[a.B + g0 + s]), wl_min)}].ids.push_back(g0 + s);   // ... the allocation class may be coarser
             }
             rows_g = std::max(rows_g, rows);
         }
