@@ -345,6 +345,9 @@ __device__ __forceinline__ void interp_row(float s, int o, int in_last, int &i0,
     w0 = __fsub_rn(1.0f, w1);
 }
 
+// gather through a packed pair of BYTE offsets (lo 16 bits | hi 16 bits): one add per address instead of unpack + scale + add
+__device__ __forceinline__ double ldb(const double *base, int byte_off) { return *(const double *)((const char *)base + byte_off); }
+
 // select element `slot` of a register array without dynamic indexing
 template <int ET> __device__ __forceinline__ double pick(const double (&v)[ET], int slot) {
     double o = 0.0;
@@ -668,7 +671,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     interp_row(s_tl, i, N_l, i0, i1, w0, w1);
                     i0 = min(i0, WLa - 1) + 1; i1 = min(i1, WLa - 1) + 1;
                     if (i > N_t) { w1 = 0.f; i0 = 0; i1 = 0; }
-                    tix[r] = i0 | (i1 << 16); twb[r] = w1;
+                    tix[r] = (i0 * 8) | ((i1 * 8) << 16); twb[r] = w1;          // byte offsets into a longitudinal row
                 }
                 for (int j = ln; j < WLp; j += L) {
                     int i0 = 0, i1 = 0; float w0 = 0.f, w1 = 0.f;
@@ -676,7 +679,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         interp_row(s_lt, j, N_t, i0, i1, w0, w1);
                         i0 = PR(min(i0, LE - 1)); i1 = PR(min(i1, LE - 1));      // qs is PR()-indexed
                     }
-                    LW[2 * j] = (double)w0; LW[2 * j + 1] = (double)w1; LI[j] = i0 | (i1 << 16);
+                    LW[2 * j] = (double)w0; LW[2 * j + 1] = (double)w1; LI[j] = (i0 * 8) | ((i1 * 8) << 16);     // byte offsets into qs
                 }
                 curNt = N_t; curNl = N_l;
               }
@@ -726,7 +729,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         const int j0 = tix[r] & 0xffff, j1 = tix[r] >> 16;
                         const float w1f = twb[r];
                         const double w1 = (double)w1f, w0 = (double)__fsub_rn(1.0f, w1f);
-                        yy[r] = w0 * (2.0 * Lb[z1o - 1 + j0] + Lb[z2o - 1 + j0]) + w1 * (2.0 * Lb[z1o - 1 + j1] + Lb[z2o - 1 + j1]);
+                        yy[r] = w0 * (2.0 * ldb(Lb + z1o - 1, j0) + ldb(Lb + z2o - 1, j0)) + w1 * (2.0 * ldb(Lb + z1o - 1, j1) + ldb(Lb + z2o - 1, j1));
                     }
                     for (int j = ln; j < WLs; j += L) Lb[zao + j] = (j <= N_l) ? 2.0 * Lb[z1o + j] - Lb[z2o + j] : 0.0;
                     double yyl = shup<L>(yy[ET - 1], 1);
@@ -788,8 +791,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                             const double z1l = (j - 1 <= N_l) ? Lb[z1o + j - 1] : 0.0, z1r = (j + 1 <= N_l) ? Lb[z1o + j + 1] : 0.0;
                             const double z2l = (j - 1 <= N_l) ? Lb[z2o + j - 1] : 0.0, z2r = (j + 1 <= N_l) ? Lb[z2o + j + 1] : 0.0;
                             const int li0 = LI[j], li1 = LI[j + 1];
-                            const double pj = LW[2 * j] * qs[li0 & 0xffff] + LW[2 * j + 1] * qs[li0 >> 16];
-                            const double pj1 = LW[2 * j + 2] * qs[li1 & 0xffff] + LW[2 * j + 3] * qs[li1 >> 16];
+                            const double pj = LW[2 * j] * ldb(qs, li0 & 0xffff) + LW[2 * j + 1] * ldb(qs, li0 >> 16);
+                            const double pj1 = LW[2 * j + 2] * ldb(qs, li1 & 0xffff) + LW[2 * j + 3] * ldb(qs, li1 >> 16);
                             v = dB * z1c + eB * (z1l + z1r) + dC * z2c + eC * (z2l + z2r) - phl * (pj1 - pj);
                         }
                         // longitudinal rows sit at padded index Nx_t1 + j >= N_t + 1: x clamps to the right end
@@ -829,7 +832,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         for (int r = 0; r < ET; r++) {
                             const int j0 = tix[r] & 0xffff, j1 = tix[r] >> 16;
                             const float w1f = twb[r];
-                            y[r] = (double)__fsub_rn(1.0f, w1f) * Lb[zco - 1 + j0] + (double)w1f * Lb[zco - 1 + j1];
+                            y[r] = (double)__fsub_rn(1.0f, w1f) * ldb(Lb + zco - 1, j0) + (double)w1f * ldb(Lb + zco - 1, j1);
                         }
                         double yl = shup<L>(y[ET - 1], 1);
                         if (ln == 0) yl = 0.0;
@@ -872,8 +875,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         if (upd) for (int j = ln; j < WLs; j += L) {
                             const int li0 = LI[j], li1 = LI[j + 1];
                             const double2 w0 = *(const double2 *)(LW + 2 * j), w1 = *(const double2 *)(LW + 2 * j + 2);
-                            const double pj = w0.x * qs[li0 & 0xffff] + w0.y * qs[li0 >> 16];
-                            const double pj1 = w1.x * qs[li1 & 0xffff] + w1.y * qs[li1 >> 16];
+                            const double pj = w0.x * ldb(qs, li0 & 0xffff) + w0.y * ldb(qs, li0 >> 16);
+                            const double pj1 = w1.x * ldb(qs, li1 & 0xffff) + w1.y * ldb(qs, li1 >> 16);
                             double rhs = PHL * (pj1 - pj);
                             if (j < keep_l) rhs -= Lb[rlo + j];
                             const double zr = (j + 1 < WLs) ? Lb[zco + j + 1] : 0.0;
