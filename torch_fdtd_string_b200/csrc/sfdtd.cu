@@ -966,8 +966,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     const double ctr = t[T_CTR], wid = t[T_WID];
                     const double hw = wid * 0.5, iw2 = 2.0 * frcp(wid);
                     bow_ic = tabi[jj * NI + I_IC];
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {
+                    auto window = [&](int c) {
                         const int i = bow_ic + c * L + ln;
                         const double x = (double)xaxs[min(i, NXT - 1)];
                         const double dm = __dsub_rn(__dsub_rn(x, ctr), hw), dp = __dadd_rn(__dsub_rn(x, ctr), hw);
@@ -975,8 +974,13 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                         double o = 0.5 * (1.0 + cospi((x - ctr) * iw2));
                         o = (p > 0 && i < NXT) ? o : ((p != p && i < NXT) ? p : 0.0);
                         if (((c == 1 && ln == L - 1) || i >= LE) && o != 0.0) status |= SFDTD_ST_BOW_WINDOW;
-                        if (c == 0) bw0 = o; else bw1 = o;
-                    }
+                        return o;
+                    };
+                    bw0 = window(0);
+                    // rows bow_ic + L ... are only inside the window when it is wider than ~L - 4 grid points (x_i = i / (Nx_t1 - 1),
+                    // one row of margin for the float32 axis); NaN parameters take the general path
+                    const bool second = !((ctr + hw) * (double)NXT + 1.0 <= (double)(bow_ic + L));
+                    if (__any_sync(FULLMASK, second)) bw1 = window(1);
                 }
                 gs_solve(rt, true, true);
                 cnt_outer += 2;      // the reference's second pass reproduces the first (residual 0)
