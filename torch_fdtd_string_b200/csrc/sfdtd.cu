@@ -22,14 +22,19 @@
 //     (misc.cpp:78-105) are gathers whose indices/weights are cached and rebuilt only when a grid
 //     size changes (a few times per second of audio).
 //   * Per-step scalars (grid sizes, loss, operator coefficients; string.cpp:16-41,96-120) are computed
-//     TB steps at a time, one step per lane, into a shared-memory table; outputs are staged there too
-//     and flushed as coalesced rows.
+//     TB steps at a time (16 in independent mode, 8 in grouped mode), one step per lane, into a shared-memory table;
+//     outputs are staged there too and flushed as coalesced rows.
 //   * Groups (reference batches) couple their strings only through the batch-max operator widths and
 //     the any-over-batch convergence votes (string.cpp:252-253, hammer.cpp:51).  The widths come from a
 //     prepass table.  A group without bowed/hammered strings needs no votes (the second fixed-point
 //     pass of an unforced string reproduces the first), so its strings run fully independently
 //     ("independent mode", any warp, no CTA barrier); a group with forced strings runs as one CTA with
 //     __syncthreads_or votes ("grouped mode").
+//   * Scheduling (independent mode): the grid of a bucket is what is resident at once, and every warp pulls its next
+//     (time slice, set of 32/L strings) item from a per-bucket counter -- the hardest sets first, each for the whole call,
+//     the sets of the last round in time slices whose state rows pass from warp to warp through global memory with a
+//     release/acquire word per set.  Loop conditions inside the time loop are kept provably warp-uniform (kernel
+//     parameters, __shfl_sync broadcasts, vote results): otherwise every shuffle is compiled with a reconvergence path.
 // No tensor cores: no step is a dense contraction.  HBM traffic: controls in, audio out.
 
 #include <cuda_runtime.h>
