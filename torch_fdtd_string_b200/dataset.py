@@ -69,12 +69,28 @@ def save_simulation_data(directory, excitation_type, simulation_dict, string_dic
         yaml.dump(short, f, default_flow_style=False)
 
 
+def _write_string(d, wavs, sr, bitrate, save, kinds, sim, string_dict, hammer_dict, bow_dict, theta_t, lambda_c):
+    os.makedirs(d, exist_ok=True)
+    for name, x in zip(("output-u.wav", "output-z.wav", "output.wav"), wavs):
+        write_wav(f"{d}/{name}", x, sr, bitrate)
+    if save:
+        save_simulation_data(d, kinds, sim, string_dict, hammer_dict, bow_dict, theta_t, lambda_c)
+
+
 def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000, length=1.0, seed=1234,
              precision="double", normalize_output=True, skip_silence=True, silence_threshold=-23.0, save=True,
-             randomize_name=False, batches_per_call=296, rank=0, world_size=1, device=None, surface_integral=True,
-             sampler_cfg=None, time_log=False):
+             randomize_name=False, batches_per_call=64, rank=0, world_size=1, device=None, surface_integral=True,
+             sampler_cfg=None, time_log=False, num_workers=4):
     """Generates ``num_samples // batch_size`` reference batches (reference run.py:109) and writes the kept strings.
-    Returns dict(strings, written, nan, silent, seconds_stepper)."""
+    The per-string files (three wavs, four compressed archives: ~0.3 s of zlib per string on one core, 3000x what the
+    stepper needs for that string) are written by ``num_workers`` threads (``proc.num_workers`` of the reference's config; zlib
+    releases the GIL) while the GPU runs the next call; at most two calls' host arrays are alive.
+    Returns dict(strings, written, nan, silent, seconds_stepper, seconds_total)."""
+    import concurrent.futures
+    import time
+    t_start = time.perf_counter()
+    pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(1, int(num_workers)))
+    pending = []
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     n_batches = num_samples // batch_size
     mine = list(rank_batches(n_batches, world_size, rank))
@@ -123,18 +139,13 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
         sig0 = res["sig0"].cpu().numpy(); sig1 = res["sig1"].cpu().numpy()
         nt_, nl_ = sampler.derived_grid(torch.from_numpy(f0), p_host["kappa"][keep].view(-1, 1), p_host["k"], p_host["theta_t"],
                                         p_host["lambda_c"], p_host["alpha"][keep].view(-1, 1))
+        new_jobs = []
         for j, b in enumerate(np.nonzero(keep)[0]):
             it = chunk[b // batch_size]; bb = b % batch_size
             if it not in names:
                 names[it] = "".join(rng.choice(_CHARS, 8)) if randomize_name else str(it)
             dx = names[it]
             d = f"{save_dir}/{dx}-{bb}"
-            os.makedirs(d, exist_ok=True)
-            write_wav(f"{d}/output-u.wav", host["u"][j], sr, bitrate)
-            write_wav(f"{d}/output-z.wav", host["z"][j], sr, bitrate)
-            write_wav(f"{d}/output.wav", host["w"][j], sr, bitrate)
-            if not save:
-                continue
             bow, ham = bool(p_host["bow_mask"][b]), bool(p_host["hammer_mask"][b])
             kinds = (["bow"] if bow else []) + (["hammer"] if ham else []) + (["pluck"] if not (bow or ham) else [])
             sim = dict(uout=raw["uout"][j], zout=raw["zout"][j], v_r_out=raw["v_r"][j], F_H_out=raw["F_H"][j],
@@ -147,9 +158,17 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
             hammer_dict = dict(x_H=T("x_H"), v_H=T("v_H"), u_H=ctl_h["u_H"][j], w_H=T("w_H"), M_r=T("M_r"), alpha=T("alpha_H"))
             bow_dict = dict(x_B=ctl_h["x_b"][j], v_B=ctl_h["v_b"][j], F_B=ctl_h["F_b"][j], phi_0=T("phi_0"), phi_1=T("phi_1"),
                             wid_B=T("wid"))
-            save_simulation_data(d, ",".join(kinds), sim, string_dict, hammer_dict, bow_dict, p_host["theta_t"], p_host["lambda_c"])
-            stats["written"] += 1
+            new_jobs.append(pool.submit(_write_string, d, (host["u"][j], host["z"][j], host["w"][j]), sr, bitrate, save,
+                                        ",".join(kinds), sim, string_dict, hammer_dict, bow_dict, p_host["theta_t"], p_host["lambda_c"]))
+            stats["written"] += 1 if save else 0
+        for fut in pending:                     # the previous call's files must be on disk before a third call's arrays pile up
+            fut.result()
+        pending = new_jobs
         del res, ctl, pp
+    for fut in pending:
+        fut.result()
+    pool.shutdown()
+    stats["seconds_total"] = time.perf_counter() - t_start
     return stats
 
 
@@ -166,11 +185,13 @@ def main():
     ap.add_argument("--no-normalize", action="store_true")
     ap.add_argument("--keep-silent", action="store_true")
     ap.add_argument("--randomize-name", action="store_true")
+    ap.add_argument("--num-workers", type=int, default=4, help="file-writer threads (proc.num_workers of the reference's config)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     st = generate(a.save_dir, a.num_samples, a.batch_size, a.excitation, a.sr, a.length, a.seed, a.precision,
-                  not a.no_normalize, not a.keep_silent, randomize_name=a.randomize_name, rank=rank, world_size=world)
+                  not a.no_normalize, not a.keep_silent, randomize_name=a.randomize_name, rank=rank, world_size=world,
+                  num_workers=a.num_workers)
     print(st)
 
 

@@ -224,7 +224,7 @@ def main(argv=None):
             bool(task["skip_silence"]), float(task["silence_threshold"]), save=bool(task.get("save", True)),
             randomize_name=bool(task["randomize_name"]), rank=rank, world_size=world,
             surface_integral=bool(task["surface_integral"]), sampler_cfg=sampler_config(task),
-            time_log=True)
+            time_log=True, num_workers=int(proc.get("num_workers") or 1))
         print(f"[run] rank {rank}/{world}: {stats}")
     return 0
 
