@@ -50,6 +50,16 @@ def test_overrides():
         H.compose(MINI, "config.yaml", ["experiment=base", "task=simulate"], now=NOW)      # base has no /task entry
 
 
+def test_defaults_keywords():
+    """optional / override / group@package entries and a nested group option (model/excitation)"""
+    cfg, _ = H.compose(MINI, "config.yaml", ["experiment=keywords", "task.result_dir=r"], now=NOW)
+    assert cfg["model"]["excitation"] == {"kind": "strike", "force": 2.5} and cfg["model"]["_name_"] == "fdtd"
+    assert cfg["task"]["more"] == {"x": 1, "y": 48000}                 # key-level package, interpolation through the root
+    assert "extra" not in cfg                                            # the optional entry does not exist: skipped
+    cfg, _ = H.compose(MINI, "config.yaml", ["experiment=keywords", "task.result_dir=r", "model/excitation=null"], now=NOW)
+    assert "excitation" not in cfg["model"] or cfg["model"]["excitation"] is None
+
+
 def test_same_group_include_and_filter():
     cfg, _ = H.compose(MINI, "config.yaml", ["experiment=tiny", "task.result_dir=r", "model=pluck"], now=NOW)
     assert cfg["model"]["_name_"] == "fdtd" and cfg["model"]["excitation"] == "pluck"
