@@ -79,7 +79,10 @@ FINEHAMMER = dict(
     bow_kwargs=dict(),
 )
 
-PRESETS = dict(nsynth=NSYNTH, allfixed=ALLFIXED, linear=LINEAR, finehammer=FINEHAMMER)
+# BASELINE config 4 at its stated rate: 192 kHz (N_t = 237, N_l = 593 with pre-correction off)
+FINEHAMMER192 = dict(FINEHAMMER, sr=192000)
+
+PRESETS = dict(nsynth=NSYNTH, allfixed=ALLFIXED, linear=LINEAR, finehammer=FINEHAMMER, finehammer192=FINEHAMMER192)
 
 CASES = dict(
     pluck_b1=dict(preset='nsynth', model='pluck', B=1, length=0.01),
@@ -98,7 +101,19 @@ CASES = dict(
     random_b24=dict(preset='nsynth', model='random', B=24, length=0.004, seed=3),
     pluck_b2_long=dict(preset='nsynth', model='pluck', B=2, length=0.1, seed=5),
     random_b4_long=dict(preset='nsynth', model='random', B=4, length=0.05, seed=9),
+    # ---- full-length runs of the BASELINE configs (long format: audio outputs only, time-constant curves stored once) ----
+    # configs[0]: single plucked string, nsynth-like, 1 s @ 48 kHz (reference ~8 min)
+    pluck_b1_1s=dict(preset='nsynth', model='pluck', B=1, length=1.0, long=True, threads=1),
+    # configs[1]: one nsynth-like reference batch at full length (reference ~2-3 h); NaN strings included
+    pluck_b24_1s=dict(preset='nsynth', model='pluck', B=24, length=1.0, long=True, threads=3, keys=('uout', 'zout')),
+    # configs[2]: bowed string, Helmholtz regime, 4 s (reference ~1 h)
+    allfixed_bow_b1_4s=dict(preset='allfixed', model='bow', B=1, length=4.0, long=True, threads=1, keys=('uout', 'zout', 'v_r_out')),
+    # configs[3]: hammered string, tension modulation, 192 kHz, first 9600 steps (reference ~13 min)
+    finehammer192_b1=dict(preset='finehammer192', model='hammer', B=1, length=0.05, long=True, threads=2),
+    # sensitivity of the reference itself: the same inputs with state_u *= 1 + 2^-50 (outputs only, merged with --merge-pert)
+    pluck_b24_01s=dict(preset='nsynth', model='pluck', B=24, length=0.1, long=True, threads=3, keys=('uout', 'zout')),
 )
+PERT = 1.0 + 2.0 ** -50
 
 
 def compact_state(x):
@@ -107,8 +122,18 @@ def compact_state(x):
     return nz.numpy().astype(np.int64), x[:, nz, :].numpy().copy()
 
 
-def run_case(name, spec):
+def compact_time(x):
+    """(B,Nt) curve -> (B,1) when it is constant in time"""
+    x = x.numpy()
+    if x.ndim == 2 and x.shape[1] > 1 and (x == x[:, :1]).all():
+        return x[:, :1].copy()
+    return x
+
+
+def run_case(name, spec, perturb=False):
     p = PRESETS[spec['preset']]
+    if spec.get('threads'):
+        torch.set_num_threads(spec['threads'])
     sr = p['sr']
     mode, kap, f0m = p['theta']
     theta_t = fdm.get_theta(kap, f0m, sr)
@@ -125,6 +150,8 @@ def run_case(name, spec):
             hammer_params=[t.clone() for t in hammer_params],
             bow_mask=bow_mask.clone(), hammer_mask=hammer_mask.clone(),
             consts=list(consts), Nt=Nt, chunk_size=chunk_size, rest=rest)
+        if perturb:
+            state_u.mul_(PERT)
         return orig_process(root_dir, state_u, state_z, string_params, bow_params, hammer_params,
                             bow_mask, hammer_mask, consts, Nt, chunk_size, *rest)
 
@@ -146,6 +173,14 @@ def run_case(name, spec):
     dt = time.time() - t0
     uout, zout, state_u, state_z, v_r, F_H, u_H_o, sig0, sig1 = res
     c = captured
+    if perturb:
+        path = os.path.join(PERT_DIR, f"{name}_pert.npz")
+        os.makedirs(PERT_DIR, exist_ok=True)
+        np.savez(path, uout=uout.numpy(), zout=zout.numpy())
+        print(f"{name} (perturbed): ref {dt:.1f}s -> {path}", flush=True)
+        return
+    if spec.get('long'):
+        return save_long(name, spec, p, c, res, params, dt)
     su_idx, su_rows = compact_state(c['state_u'])
     sz_idx, sz_rows = compact_state(c['state_z'])
     sp = c['string_params']; bp = c['bow_params']; hp = c['hammer_params']
@@ -179,7 +214,74 @@ def run_case(name, spec):
           f"{os.path.getsize(path) / 1024:.0f} KiB; |uout|max={np.abs(out['uout']).max():.3e}", flush=True)
 
 
+PERT_DIR = os.path.join(ROOT, "gpurun_out", "golden_pert")     # scratch (git-ignored): raw outputs of the perturbed runs
+
+
+def save_long(name, spec, p, c, res, params, dt):
+    """Long format: compact inputs (time-constant curves once, non-zero state rows / u_H columns only), audio outputs."""
+    uout, zout, state_u, state_z, v_r, F_H, u_H_o, sig0, sig1 = res
+    su_idx, su_rows = compact_state(c['state_u'])
+    sz_idx, sz_rows = compact_state(c['state_z'])
+    sp = c['string_params']; bp = c['bow_params']; hp = c['hammer_params']
+    B, Nt, Nx_t1 = c['state_u'].shape
+    uH = hp[2]
+    uH_idx = (uH != 0).any(dim=0).nonzero().view(-1)
+    outs = dict(uout=uout, zout=zout, v_r_out=v_r, F_H_out=F_H, u_H_out=u_H_o)
+    out = dict(
+        long_format=True,
+        B=B, Nt=Nt, Nx_t1=Nx_t1, Nx_l1=c['state_z'].shape[2], sr=p['sr'],
+        chunk_size=c['chunk_size'], consts=np.array(c['consts'], dtype=np.float64),
+        relative_order=p['relative_order'], surface_integral=spec.get('surface_integral', True),
+        manufactured=spec.get('manufactured', False),
+        state_u_idx=su_idx, state_u_rows=su_rows, state_z_idx=sz_idx, state_z_rows=sz_rows,
+        kappa=sp[0].numpy(), alpha=sp[1].numpy(), p_a=sp[4].numpy(), f0=compact_time(sp[5]), pos=sp[6].numpy(),
+        T60=sp[7].numpy(),
+        x_b=compact_time(bp[0]), v_b=compact_time(bp[1]), F_b=compact_time(bp[2]), phi_0=bp[3].numpy(), phi_1=bp[4].numpy(),
+        wid=compact_time(bp[5]),
+        x_H=hp[0].numpy(), u_H_idx=uH_idx.numpy().astype(np.int64), u_H_cols=uH[:, uH_idx].numpy().copy(),
+        w_H=hp[3].numpy(), M_r=hp[4].numpy(), alpha_H=hp[5].numpy(),
+        bow_mask=c['bow_mask'].numpy(), hammer_mask=c['hammer_mask'].numpy(),
+        sig0=sig0.numpy(), sig1=sig1.numpy(),
+        state_u_last=state_u[:, -2:, :].numpy(), state_z_last=state_z[:, -2:, :].numpy(),
+        ref_seconds=dt,
+    )
+    for k in spec.get('keys', tuple(outs)):
+        out[k] = outs[k].numpy()
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    nan = np.isnan(out['uout']).any(axis=1)
+    print(f"{name}: B={B} Nt={Nt} Nx_t1={Nx_t1} Nx_l1={out['Nx_l1']} ref {dt:.1f}s -> "
+          f"{os.path.getsize(path) / 1024:.0f} KiB; NaN strings {int(nan.sum())}/{B}", flush=True)
+
+
+def merge_pert(name, win=480):
+    """Adds the reference's own sensitivity to fixture `name`: per string and per window of `win` samples, the distance
+    between the reference run and the reference run on state_u * (1 + 2^-50), plus the NaN onsets of the perturbed run."""
+    path = os.path.join(HERE, f"{name}.npz")
+    g = dict(np.load(path))
+    q = np.load(os.path.join(PERT_DIR, f"{name}_pert.npz"))
+    for k in ('uout', 'zout'):
+        a, b = g[k], q[k]
+        n = a.shape[1] // win * win
+        d = np.nan_to_num(b[:, :n] - a[:, :n] * PERT, nan=0.0, posinf=0.0, neginf=0.0).reshape(a.shape[0], -1, win)
+        r = np.nan_to_num(a[:, :n], nan=0.0, posinf=0.0, neginf=0.0).reshape(a.shape[0], -1, win)
+        g[f'pert_{k}_err'] = np.sqrt((d ** 2).sum(-1))            # (B, n_win) absolute L2 distance per window
+        g[f'pert_{k}_norm'] = np.sqrt((r ** 2).sum(-1))
+        bad = ~np.isfinite(b)
+        g[f'pert_{k}_nan_onset'] = np.where(bad.any(1), bad.argmax(1), -1).astype(np.int64)
+    g['pert_win'] = win
+    np.savez_compressed(path, **g)
+    print(f"{name}: merged perturbed-run sensitivity ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES)
-    for nm in names:
-        run_case(nm, CASES[nm])
+    argv = sys.argv[1:]
+    if argv and argv[0] == "--merge-pert":
+        for nm in argv[1:]:
+            merge_pert(nm)
+    elif argv and argv[0] == "--perturbed":
+        for nm in argv[1:]:
+            run_case(nm, CASES[nm], perturb=True)
+    else:
+        for nm in (argv or [k for k, v in CASES.items() if not v.get('long')]):
+            run_case(nm, CASES[nm])

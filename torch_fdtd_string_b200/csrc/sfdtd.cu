@@ -38,6 +38,7 @@
 // No tensor cores: no step is a dense contraction.  HBM traffic: controls in, audio out.
 
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -57,6 +58,8 @@
 #endif
 
 #define FULLMASK 0xffffffffu
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -98,11 +101,27 @@ enum { I_NT = 0, I_NL, I_R, I_WLS, I_RK, I_KEEPL, I_IDXH, I_IC };
 // per-string constants
 enum { C_WPOW = 0, C_MR, C_AHM1, C_PHI0, C_PHI1, C_RP };
 
+// grouped mode: what one CTA of a group's cluster runs.  A group (reference batch) is spread over the CTAs of one
+// thread-block cluster; `cls` selects the lane/row shape of all string slots of this CTA.
+constexpr int CTA_SLOTS = 8;
+struct CtaDesc {
+    int32_t group;                  // group id (row of Wtab)
+    int32_t cls;                    // 0: 16 lanes x 4 rows per string, 1: 32 lanes x 4 rows
+    int32_t n;                      // string slots in use
+    int32_t G;                      // strings of the group
+    int32_t str[CTA_SLOTS];         // global string id per slot
+    int32_t gidx[CTA_SLOTS];        // index of the string inside its group (its entry of the group board)
+};
+
 struct KArgs {
     sfdtd_args a;
+    sfdtd_synth sy;                 // copy of *a.synth (valid when has_synth)
+    int32_t has_synth;
     double k, ik, k2, k4, th, omth, tt1, tt2, lamc, order, mhd;
     const int32_t *Wtab;            // [n_groups][Nt]  W_t | W_l << 16  (batch-max operator widths, misc.cpp:119-127)
-    const int32_t *ids;             // independent mode: string ids; grouped mode: group ids
+    const int32_t *ids;             // independent mode: string ids
+    const CtaDesc *ctas;            // grouped mode: one descriptor per CTA
+    double *uH_carry;               // (B,2) hammer displacement rows [n-2, n-1] handed over between time slices when a.u_H.ptr is NULL
     int32_t n_items;                // entries of ids
     const int32_t *maxNl;           // per string: largest N_l of this call (prepass); sizes the longitudinal block in grouped mode
     int32_t WLp;                    // independent mode: longitudinal rows allocated per string (incl. guards)
@@ -120,6 +139,54 @@ __device__ __forceinline__ double ldx(const sfdtd_array &A, int b, int n) {
 }
 __device__ __forceinline__ double lds(const sfdtd_array &A, int b) {
     return ((const double *)A.ptr)[(int64_t)b * A.bs];
+}
+
+// ---- control curves: read from the caller's (B,Nt) arrays, or synthesised from per-string scalars (sfdtd_synth) -------
+// Every kernel evaluates the same functions with explicitly rounded operations (no FMA contraction), so the prepass,
+// the width table, the stepper and sfdtd_synth_controls see bit-identical values (floor(1/h) of f0 decides grid sizes).
+__device__ __forceinline__ double sy_ramp(const sfdtd_synth &y, int g) {      // g: global 0-based sample index
+    const int den = y.Nt_full > 1 ? y.Nt_full - 1 : 1;
+    return __ddiv_rn((double)g, (double)den);
+}
+__device__ __forceinline__ double sy_lin(double a, double b, double ramp) { return __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), ramp)); }
+__device__ __forceinline__ double sy_f0(const sfdtd_synth &y, int b, int g) {
+    const double f = sy_lin(y.f0_a[b], y.f0_b[b], sy_ramp(y, g));
+    const double dt = __dsub_rn((double)(g + 1), y.vib_t0[b]);
+    double vib = 0.0;
+    if (dt > 0) {
+        const double ph = __dmul_rn(__dmul_rn(__dmul_rn(2 * M_PI, y.mod_frq[b]), dt), __ddiv_rn(1.0, y.sr));
+        vib = __ddiv_rn(__dmul_rn(y.mod_amp[b], __dsub_rn(1.0, cos(ph))), 2.0);
+    }
+    return __dadd_rn(f, __dmul_rn(vib, f));
+}
+__device__ __forceinline__ double sy_xb(const sfdtd_synth &y, int b, int g) { return sy_lin(y.x_b1[b], y.x_b2[b], sy_ramp(y, g)); }
+__device__ __forceinline__ double sy_vb(const sfdtd_synth &y, int b, int g) {
+    return __dmul_rn(sy_lin(y.v_b1[b], y.v_b2[b], sy_ramp(y, g)), tanh(__dmul_rn(__ddiv_rn((double)(g + 1), y.sr), 10.0)));
+}
+__device__ __forceinline__ double sy_Fb(const sfdtd_synth &y, int b, int g) {
+    double F = sy_lin(y.F_b1[b], y.F_b2[b], sy_ramp(y, g));
+    const double po = y.pulloff[b];
+    if (po > 0) {
+        const double off = __dsub_rn((double)y.Nt_full, floor(__dmul_rn(y.sr, po)));
+        const double rem = fmax(__dsub_rn(__dsub_rn((double)y.Nt_full, (double)g), off), 0.0);
+        F = __dmul_rn(F, tanh(__dmul_rn(__ddiv_rn(rem, y.sr), 100.0)));
+    }
+    return F;
+}
+__device__ __forceinline__ double sy_uH(const sfdtd_synth &y, int b, int g) {
+    if (g == 0) return -1e-3;
+    if (g == 1) return __dadd_rn(-1e-3, __dmul_rn(__ddiv_rn(1.0, y.sr), y.v_H[b]));
+    return 0.0;
+}
+__device__ __forceinline__ double ctl_f0(const KArgs &A, int b, int n) { return A.has_synth ? sy_f0(A.sy, b, n + A.sy.t_0) : ldx(A.a.f0, b, n); }
+__device__ __forceinline__ double ctl_xb(const KArgs &A, int b, int n) { return A.has_synth ? sy_xb(A.sy, b, n + A.sy.t_0) : ldx(A.a.x_b, b, n); }
+__device__ __forceinline__ double ctl_vb(const KArgs &A, int b, int n) { return A.has_synth ? sy_vb(A.sy, b, n + A.sy.t_0) : ldx(A.a.v_b, b, n); }
+__device__ __forceinline__ double ctl_Fb(const KArgs &A, int b, int n) { return A.has_synth ? sy_Fb(A.sy, b, n + A.sy.t_0) : ldx(A.a.F_b, b, n); }
+__device__ __forceinline__ double ctl_wid(const KArgs &A, int b, int n) { return A.has_synth ? A.sy.wid[b] : ldx(A.a.wid, b, n); }
+// pre-loaded content of hammer_params[2] at sample n (string.cpp:303 adds the new displacement onto it)
+__device__ __forceinline__ double ctl_uH(const KArgs &A, int b, int n) {
+    if (A.a.u_H.ptr) return ldx(A.a.u_H, b, n);
+    return A.has_synth ? sy_uH(A.sy, b, n + A.sy.t_0) : 0.0;
 }
 
 // 1/x to full double precision without the slow-path branch of the IEEE division (MUFU.RCP64H + 2 Newton steps)
@@ -175,10 +242,10 @@ __global__ void sfdtd_prepass_kernel(const __grid_constant__ KArgs A, int32_t *m
     }
     __shared__ double sd[32];
     if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = dm;
-    if (A.a.f0.ts == 0) {
+    if (!A.has_synth && A.a.f0.ts == 0) {
         fm = ldx(A.a.f0, b, 0);
     } else {
-        for (int n = 2 + threadIdx.x; n < Nt; n += blockDim.x) { const double v = ldx(A.a.f0, b, n); fm = v < fm ? v : fm; }
+        for (int n = 2 + threadIdx.x; n < Nt; n += blockDim.x) { const double v = ctl_f0(A, b, n); fm = v < fm ? v : fm; }
     }
     for (int o = 16; o > 0; o >>= 1) { const double v = __shfl_xor_sync(FULLMASK, fm, o); fm = v < fm ? v : fm; }
     __shared__ double sm[32];
@@ -207,7 +274,7 @@ __global__ void sfdtd_width_kernel(const __grid_constant__ KArgs A, int32_t *Wta
     int wt = 0, wl = 0;
     for (int s = 0; s < G; s++) {
         const int b = g0 + s;
-        const Derived d = derive(ldx(A.a.f0, b, n), lds(A.a.kappa, b), lds(A.a.alpha, b), A);
+        const Derived d = derive(ctl_f0(A, b, n), lds(A.a.kappa, b), lds(A.a.alpha, b), A);
         wt = max(wt, clampN(d.Nt)); wl = max(wl, clampN(d.Nl));
     }
     Wtab[(int64_t)g * Nt + n] = (wt + 1) | ((wl + 1) << 16);
@@ -230,7 +297,52 @@ template <int L> __device__ __forceinline__ int red_or(int v) {
 // any-over-CTA vote.  The barrier reduction returns the same value to every thread, but the compiler does not treat it as
 // warp-uniform: a loop that exits on it would count as divergent and every shuffle inside would be compiled with a
 // reconvergence sequence.  Passing it through a warp vote makes the uniformity visible.
-__device__ __forceinline__ int cta_or(int pred) { return __any_sync(FULLMASK, __syncthreads_or(pred)); }
+// ---- group board (grouped mode): what the strings of one group publish to each other ------------------------------
+// A group (reference batch) runs as one thread-block cluster of 128-thread CTAs.  The board is replicated at the start
+// of every CTA's shared memory and written through distributed shared memory:
+//   vote words   [2][8]          any-over-group votes, one word per CTA of the cluster, two phases
+//   step scalars [GB_MAX][6]     inputs of the hammer contact loop (hammer.cpp:28-53), published once per time step
+//   eps_u        [2][GB_MAX]     string displacement at the contact point of the current iterate, two phases
+// With the contact-loop inputs on every CTA's board, every WARP runs the scalar contact loops of all strings of the group
+// itself (one string per lane, warp votes) -- the any-over-batch vote of hammer.cpp:51 costs no barrier at all, and a time
+// step needs 1 + (outer iterations) cluster barriers instead of one per contact-loop and outer iteration.
+constexpr int GB_MAX = 64;                          // strings per group (<= 8 CTAs x 8 slots)
+constexpr int GB_HQ = GB_MAX / 32;                  // strings per lane in the warp-redundant contact loop
+constexpr int GB_VOTE = 0, GB_STEP = 8, GB_EPS = GB_STEP + 6 * GB_MAX, GB_DOUBLES = GB_EPS + 2 * GB_MAX;
+enum { GS_ETA1 = 0, GS_ETA2, GS_WR, GS_BASE, GS_HM, GS_TOLT };
+
+struct GroupComm {
+    double *board;          // this CTA's board
+    int cs, rank;           // cluster size, rank of this CTA
+    int phase;              // vote phase (CTA-uniform)
+    __device__ __forceinline__ void init(double *smem_base) {
+        board = smem_base; phase = 0;
+        cg::cluster_group cl = cg::this_cluster();
+        cs = (int)cl.num_blocks(); rank = (int)cl.block_rank();
+    }
+    __device__ __forceinline__ void sync() const {
+        if (cs > 1) cg::this_cluster().sync(); else __syncthreads();
+    }
+    // one double into slot `off` of every CTA's board (visible after the next sync())
+    __device__ __forceinline__ void publish(int off, double v) const {
+        if (cs > 1) {
+            cg::cluster_group cl = cg::this_cluster();
+            for (int r = 0; r < cs; r++) cl.map_shared_rank(board, r)[off] = v;
+        } else board[off] = v;
+    }
+    // any-over-group vote; also makes everything published before it visible
+    __device__ __forceinline__ int vote(int pred) {
+        const int v = __syncthreads_or(pred);
+        if (cs == 1) return __any_sync(FULLMASK, v);
+        int *vw = (int *)(board + GB_VOTE) + 8 * phase;
+        if ((int)threadIdx.x < cs) cg::this_cluster().map_shared_rank(vw, threadIdx.x)[rank] = v;
+        cg::this_cluster().sync();
+        int r = 0;
+        for (int q = 0; q < cs; q++) r |= vw[q];
+        phase ^= 1;
+        return __any_sync(FULLMASK, r);
+    }
+};
 template <int L> constexpr int ilog2() { return L <= 1 ? 0 : 1 + ilog2<L / 2>(); }
 
 // |x| as the high word of the double: monotone in |x| for integer compares; NaN and inf sort above every finite value
@@ -391,8 +503,8 @@ __host__ __device__ inline int slot_long_doubles(int W, bool grouped, int L) {
 __host__ __device__ inline int long_rows(int maxNl) { return (maxNl + 1 + WL_MARGIN + 2 + 1) & ~1; }   // + 2 guards, even
 
 // ======================================================================================================
-template <int L, int ET, bool GROUPED, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_constant__ KArgs A) {
+template <int L, int ET, bool GROUPED>
+__device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
     constexpr int TB = GROUPED ? TBS_G : TBS_I;
     constexpr int LE = L * ET;
     constexpr int NLA = GROUPED ? NLA_G : NLA_I;
@@ -409,12 +521,12 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
     const int sl = tid / L, ln = tid % L;
     const int nslots = blockDim.x / L;
     int b; bool valid;
+    int gi = 0, G = 1, wrow = 0;                 // grouped mode: index in the group, group size; row of the width table
+    GroupComm gc;
     if (GROUPED) {
-        const int gid = A.ids[blockIdx.x];
-        const int g0 = gid * a.group_size;
-        const int G = min(a.group_size, a.B - g0);
-        valid = sl < G;
-        b = g0 + (valid ? sl : G - 1);           // spare slots shadow the last string and never write or vote
+        valid = sl < cd->n;
+        const int s_ = valid ? sl : cd->n - 1;   // spare slots shadow the last string and never write, publish or vote
+        b = cd->str[s_]; gi = cd->gidx[s_]; G = cd->G; wrow = cd->group;
     } else {
         const int item = blockIdx.x * nslots + sl;
         valid = item < A.n_items;
@@ -430,8 +542,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
     uint32_t status = 0;
 
     // ---- shared memory carve-up: [bow axis][fixed slot parts][longitudinal parts] ----
-    float *xaxs = (float *)smem;                                      // [NXT] (only when the bow axis is needed)
-    const int xoff = A.need_xax ? (((NXT + 3) / 4) * 2) : 0;
+    if (GROUPED) gc.init(smem);
+    constexpr int O_BOARD = GROUPED ? GB_DOUBLES : 0;
+    float *xaxs = (float *)(smem + O_BOARD);                          // [NXT] (only when the bow axis is needed)
+    const int xoff = O_BOARD + (A.need_xax ? (((NXT + 3) / 4) * 2) : 0);
     double *const S = smem + xoff + (size_t)sl * slot_fixed_doubles(L, ET, GROUPED);
     double *Lb = smem + xoff + (size_t)nslots * slot_fixed_doubles(L, ET, GROUPED);
     int WLp;
@@ -516,8 +630,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
     const bool forced = bowm || hamm;
     bool group_has_hammer = false, group_has_bow = false;
     if (GROUPED) {
-        group_has_hammer = cta_or(valid && hamm);
-        group_has_bow = cta_or(valid && bowm);
+        group_has_hammer = gc.vote(valid && hamm);
+        group_has_bow = gc.vote(valid && bowm);
     }
     // CTA-uniform compute switches (they guard shuffles and barriers); per-string output switches
     const bool do_bow = group_has_bow || !skip_aux, do_ham = group_has_hammer || !skip_aux;
@@ -554,7 +668,11 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
         }
     }
     double uH1 = 0.0, uH2 = 0.0;
-    if (Nt > 2) { const int n_lo = qst[0]; uH2 = ldx(a.u_H, b, n_lo - 2); uH1 = ldx(a.u_H, b, n_lo - 1); }
+    if (Nt > 2) {
+        const int n_lo = qst[0];
+        if (a.u_H.ptr || n_lo == 2) { uH2 = ctl_uH(A, b, n_lo - 2); uH1 = ctl_uH(A, b, n_lo - 1); }
+        else { uH2 = A.uH_carry[2 * (int64_t)b]; uH1 = A.uH_carry[2 * (int64_t)b + 1]; }     // handed over by the previous time slice
+    }
     uint32_t cnt_outer = 0, cnt_sweeps = 0, cnt_ham = 0, cnt_steps = 0;
     // cached interpolation rows of Int_tl for this lane's transverse rows (rebuilt when a grid size changes):
     // indices are stored +1 so that 0 addresses the zero guard (rows beyond N_t)
@@ -575,13 +693,13 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
             const double alpha2 = alpha * alpha;
             const double xH = lds(a.x_H, b);
             const double exc = 1.0 + (hamm ? 1.0 : 0.0) + (bowm ? 1.0 : 0.0);
-            const int32_t *Wrow = A.Wtab + (int64_t)(b / a.group_size) * Nt;
+            const int32_t *Wrow = A.Wtab + (int64_t)(GROUPED ? wrow : b / a.group_size) * Nt;
             for (int s = ln; s < TB; s += L) {
                 const int n = n0 + s;
                 if (n >= n_hi) break;
                 double *t = tab + s * NV;
                 int *ti = tabi + s * NI;
-                const double f0 = ldx(a.f0, b, n);
+                const double f0 = ctl_f0(A, b, n);
                 const Derived d = derive(f0, kappa_rel, alpha, A);
                 const int N_t = clampN(d.Nt), N_l = clampN(d.Nl);
                 const int32_t w = Wrow[n];
@@ -610,7 +728,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 const double dA = (1 + s0k) + 2 * s1k * ihl2, eA = -s1k * ihl2, idA = 1.0 / dA;
                 // bow window on the Nx_t1-point axis (bow.cpp:32, misc.cpp:20-34)
                 const double Nd = (double)NXT;
-                const double xb = ldx(a.x_b, b, n), wd = ldx(a.wid, b, n);
+                const double xb = ctl_xb(A, b, n), wd = ctl_wid(A, b, n);
                 const double ctr = __ddiv_rn(__dmul_rn(xb, (double)(N_t - 1)), Nd);
                 const double wid = __ddiv_rn(__dmul_rn(__dmul_rn(wd, d.ht), (double)(N_t - 1)), Nd);
                 const int ic = (int)fmin(fmax(floor((ctr - wid * 0.5) * Nd) - 2, 0.0), 60000.0);
@@ -642,10 +760,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 t[T_PH2] = phi * iht2; t[T_PHL] = (phi != 0.0) ? ihl * d.ht : 0.0;
                 t[T_IDA] = idA; t[T_EIDA] = eA * idA;
                 t[T_RDW] = ((0.5 * d.ht) * exc) * A.ik;                      // surface-integral weight / k (string.cpp:274-291)
-                if (GROUPED) { t[T_TOLT] = pow(d.ht, A.order); t[T_TOLL] = pow(d.hl, A.order); t[T_FB] = ldx(a.F_b, b, n); }
+                if (GROUPED) { t[T_TOLT] = pow(d.ht, A.order); t[T_TOLL] = pow(d.hl, A.order); t[T_FB] = ctl_Fb(A, b, n); }
                 t[T_CTR] = ctr; t[T_WID] = wid;
-                t[T_VB] = ldx(a.v_b, b, n);
-                t[T_UHPRE] = ldx(a.u_H, b, n);
+                t[T_VB] = ctl_vb(A, b, n);
+                t[T_UHPRE] = ctl_uH(A, b, n);
                 t[T_S0K] = s0k; t[T_S1K] = s1k; t[T_GA2] = g * alpha2;
                 ti[I_NT] = N_t; ti[I_NL] = N_l; ti[I_R] = R | (oob << 30); ti[I_WLS] = WLs;
                 ti[I_RK] = min(R, keep_flat); ti[I_KEEPL] = keep_flat - NXT;
@@ -752,7 +870,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 MsStep ms;
                 if (manuf) {
                     const float tf = (float)(n + a.n_0) * a.k;                    // float32 product (string.cpp:229)
-                    const double gamma = 2.0 * ldx(a.f0, b, n);
+                    const double gamma = 2.0 * ctl_f0(A, b, n);
                     ms = ms_step(gamma, t[T_S0K] / (2.0 * A.k), gamma * lds(a.kappa, b), lds(a.p_a, b), (double)tf, A.k2);
                     const int Rk = tabi[jj * NI + I_RK];
                     const double two_ht = 2.0 / t[T_IHT];
@@ -1052,6 +1170,19 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 for (int r = 0; r < ET; r++) nu[r] = S[u1o + PRL(r)];
                 for (int j = ln; j < WLa; j += L) Lb[zpo + j] = Lb[z1o + j];
                 __syncwarp();
+                // contact-loop inputs of this string onto the board of every CTA of the group (once per step)
+                const double hbase = (2 * uH1) - uH2;
+                if (GROUPED && group_has_hammer) {
+                    const double eps0 = fetch_row<L, ET>(nu, idxH);
+                    if (ln == 0 && valid) {
+                        const int o = GB_STEP + 6 * gi;
+                        gc.publish(o + GS_ETA1, eta1); gc.publish(o + GS_ETA2, eta2);
+                        gc.publish(o + GS_WR, cst[C_WPOW] * r1pow); gc.publish(o + GS_BASE, hbase);
+                        gc.publish(o + GS_HM, hm); gc.publish(o + GS_TOLT, tol_t);
+                        gc.publish(GB_EPS + gi, eps0);
+                    }
+                    gc.sync();
+                }
                 int iter = 0;
                 bool solved = false;
                 while (true) {
@@ -1070,31 +1201,62 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                             acc += rcv * (dd * ik - vB);
                         }
                         vrel = red_sum<L>(acc);
-                        const double sg = (vrel > 0) ? 1.0 : ((vrel < 0) ? -1.0 : 0.0);
-                        const double phi0 = cst[C_PHI0], phi1 = cst[C_PHI1];
-                        hb = (vrel != vrel) ? vrel : sg * (phi1 + (1 - phi1) * exp(-phi0 * fabs(vrel)));
+                        // the friction curve only enters the right-hand side of bowed strings (string.cpp:225)
+                        if (bowm) {
+                            const double sg = (vrel > 0) ? 1.0 : ((vrel < 0) ? -1.0 : 0.0);
+                            const double phi0 = cst[C_PHI0], phi1 = cst[C_PHI1];
+                            hb = (vrel != vrel) ? vrel : sg * (phi1 + (1 - phi1) * exp(-phi0 * fabs(vrel)));
+                        }
                     }
-                    // hammer loop (hammer.cpp:28-53), votes over the group
-                    if (do_ham) {
-                        const double eps_u = fetch_row<L, ET>(nu, idxH);
-                        const double wpow = cst[C_WPOW];
-                        double eta_est = eta1 * hm;
+                    // hammer loop (hammer.cpp:28-53); its exit test is an any-over-batch vote
+                    if (do_ham && GROUPED && group_has_hammer) {
+                        // every warp iterates the scalar loops of ALL strings of the group (lane q: strings q, q + 32)
+                        const double *bd = gc.board + GB_STEP, *be = gc.board + GB_EPS + (iter & 1) * GB_MAX;
+                        const int lane = tid & 31;
+                        // (the loop inputs are re-read from the board every pass: registers are scarce here, the loop runs 1-3 passes)
+                        double est[GB_HQ], fq[GB_HQ], uq[GB_HQ];
+                        int qi[GB_HQ];
+#pragma unroll
+                        for (int h = 0; h < GB_HQ; h++) {
+                            qi[h] = min(lane + 32 * h, G - 1);
+                            est[h] = bd[6 * qi[h] + GS_ETA1] * bd[6 * qi[h] + GS_HM]; fq[h] = 0.0; uq[h] = 0.0;
+                        }
                         int hit = 0, more;
                         do {
-                            const double eta = eta_est;
-                            const double fH = ((wpow * r1pow) * (eta + eta2)) / 2;
-                            FH = (eta1 > 0) ? fH : 0.0;
-                            double v = ((2 * uH1) - uH2) - k2 * FH;
-                            double tt = v - A.mhd;
-                            tt = tt > 0 ? tt : (tt != tt ? tt : 0.0);
-                            uH = tt + A.mhd;
-                            eta_est = (uH - eps_u) * hm;
-                            const int nc = fabs(eta - eta_est) > tol_t;
+                            int nc = 0;
+#pragma unroll
+                            for (int h = 0; h < GB_HQ; h++) {
+                                const double *bq = bd + 6 * qi[h];
+                                const double eta = est[h];
+                                const double fH = (bq[GS_WR] * (eta + bq[GS_ETA2])) / 2;
+                                fq[h] = (bq[GS_ETA1] > 0) ? fH : 0.0;
+                                double tt = (bq[GS_BASE] - k2 * fq[h]) - A.mhd;
+                                tt = tt > 0 ? tt : (tt != tt ? tt : 0.0);
+                                uq[h] = tt + A.mhd;
+                                est[h] = (uq[h] - be[qi[h]]) * bq[GS_HM];
+                                nc |= (lane + 32 * h < G) && (fabs(eta - est[h]) > bq[GS_TOLT]);
+                            }
                             hit++;
-                            more = group_has_hammer ? cta_or(valid && nc) : __any_sync(FULLMASK, nc);
+                            more = __any_sync(FULLMASK, nc);
                             if (hit >= A.max_iter) { if (more) status |= SFDTD_ST_HAMMER_CAP; more = 0; }
                         } while (more);
                         cnt_ham += hit;
+                        // this string's force and hammer displacement sit in lane gi % 32
+                        double f0v = __shfl_sync(FULLMASK, fq[0], gi & 31), u0v = __shfl_sync(FULLMASK, uq[0], gi & 31);
+#pragma unroll
+                        for (int h = 1; h < GB_HQ; h++) {
+                            const double f1v = __shfl_sync(FULLMASK, fq[h], gi & 31), u1v = __shfl_sync(FULLMASK, uq[h], gi & 31);
+                            if ((gi >> 5) == h) { f0v = f1v; u0v = u1v; }
+                        }
+                        FH = f0v; uH = u0v;
+                    } else if (do_ham) {
+                        // no hammered string in the group: eta = 0 for every string, the loop ends after one pass
+                        const double fH = ((cst[C_WPOW] * r1pow) * (0.0 + eta2)) / 2;
+                        FH = (eta1 > 0) ? fH : 0.0;
+                        double tt = (hbase - k2 * FH) - A.mhd;
+                        tt = tt > 0 ? tt : (tt != tt ? tt : 0.0);
+                        uH = tt + A.mhd;
+                        cnt_ham += 1;
                     }
                     // ---- linear solve  A w = -(RHS)  ----
                     const bool need = !solved || forced;
@@ -1142,7 +1304,12 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                     // a string whose linear iteration diverges has no fixed point to wait for: it does not vote
                     const int not_conv = !capped && ((nc_t && !nan_u) || (nc_l && !nan_z));
                     iter++;
-                    int more = cta_or(valid && not_conv);
+                    if (GROUPED && group_has_hammer) {
+                        // contact-point displacement of the new iterate for the next pass (made visible by the vote's barrier)
+                        const double epsn = fetch_row<L, ET>(nu, idxH);
+                        if (ln == 0 && valid) gc.publish(GB_EPS + (iter & 1) * GB_MAX + gi, epsn);
+                    }
+                    int more = gc.vote(valid && not_conv);
                     if (iter >= A.max_iter) { if (more) status |= SFDTD_ST_OUTER_CAP; more = 0; }
                     if (!more) break;
                 }
@@ -1200,12 +1367,13 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 #pragma unroll
                     for (int r = 0; r < ET; r++) {
                         const int i = i0row + r;
-                        if (i < NXT) { nu[r] += su[i]; if (valid) su[i] = nu[r]; }
+                        // (spare slots shadow a real string: they must not read rows its owner is writing)
+                        if (i < NXT && valid) { nu[r] += su[i]; su[i] = nu[r]; }
                     }
                     double *sz = (double *)a.state_z.ptr + (int64_t)b * a.state_z.bs + (int64_t)n * a.state_z.ts;
                     __syncwarp();
                     for (int j = ln; j < WLa; j += L) {
-                        if (j < NXL) { const double row = Lb[zno + j] + sz[j]; if (valid) sz[j] = row; Lb[zno + j] = row; }
+                        if (j < NXL && valid) { const double row = Lb[zno + j] + sz[j]; sz[j] = row; Lb[zno + j] = row; }
                     }
                     ext1 = WLa;
                 }
@@ -1231,10 +1399,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
                 const double *o = ost + s * NOUT;
                 ((double *)a.uout.ptr)[(int64_t)b * a.uout.bs + (int64_t)n * a.uout.ts] = o[0];
                 ((double *)a.zout.ptr)[(int64_t)b * a.zout.bs + (int64_t)n * a.zout.ts] = o[1];
-                ((double *)a.v_r.ptr)[(int64_t)b * a.v_r.bs + (int64_t)n * a.v_r.ts] = o[2];
-                ((double *)a.F_H.ptr)[(int64_t)b * a.F_H.bs + (int64_t)n * a.F_H.ts] = o[3];
-                ((double *)a.u_H.ptr)[(int64_t)b * a.u_H.bs + (int64_t)n * a.u_H.ts] = o[4];
-                ((double *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)n * a.u_H_out.ts] = o[4] * ik;
+                if (a.v_r.ptr) ((double *)a.v_r.ptr)[(int64_t)b * a.v_r.bs + (int64_t)n * a.v_r.ts] = o[2];
+                if (a.F_H.ptr) ((double *)a.F_H.ptr)[(int64_t)b * a.F_H.bs + (int64_t)n * a.F_H.ts] = o[3];
+                if (a.u_H.ptr) ((double *)a.u_H.ptr)[(int64_t)b * a.u_H.bs + (int64_t)n * a.u_H.ts] = o[4];
+                if (a.u_H_out.ptr) ((double *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)n * a.u_H_out.ts] = o[4] * ik;
             }
         }
         __syncwarp();
@@ -1254,13 +1422,14 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
             for (int j = ln; j < WLa; j += L) if (j < NXL) { sz[j] = Lb[z2o + j]; sz[a.state_z.ts + j] = Lb[z1o + j]; }
         }
         // u_H_out / u_H columns 0,1 (simulator.cpp:57 divides the whole tensor)
-        if (ln < 2 && ln < Nt && qst[0] == 2) {
-            ((double *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)ln * a.u_H_out.ts] = ldx(a.u_H, b, ln) * A.ik;
+        if (ln < 2 && ln < Nt && qst[0] == 2 && a.u_H_out.ptr) {
+            ((double *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)ln * a.u_H_out.ts] = ctl_uH(A, b, ln) * A.ik;
         }
+        if (ln == 0 && !a.u_H.ptr && A.uH_carry) { A.uH_carry[2 * (int64_t)b] = uH2; A.uH_carry[2 * (int64_t)b + 1] = uH1; }
         if (ln == 0) {
             if (Nt > 2 && qst[1] == Nt) {
                 // loss parameters of the last step (string.cpp:119-120)
-                const Derived d = derive(ldx(a.f0, b, Nt - 1), lds(a.kappa, b), lds(a.alpha, b), A);
+                const Derived d = derive(ctl_f0(A, b, Nt - 1), lds(a.kappa, b), lds(a.alpha, b), A);
                 const double *T60 = (const double *)a.T60.ptr + (int64_t)b * a.T60.bs;
                 const double T00 = T60[0], T01 = T60[1], T10 = T60[2], T11 = T60[3];
                 const double g2 = d.gamma * d.gamma, g4 = g2 * g2;
@@ -1295,6 +1464,102 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
     }   // work-queue loop
 }
 
+// independent mode: strings of unforced groups, any warp of any CTA
+template <int L, int ET, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_constant__ KArgs A) {
+    step_body<L, ET, false>(A, nullptr);
+}
+// grouped mode: one thread-block cluster of 128-thread CTAs per group; the CTA's descriptor picks the lane/row shape of its
+// string slots.  KIND 0: strings of <= 64 rows on 16 lanes x 4 rows, <= 128 rows on 32 lanes x 4 rows (168 registers, three
+// CTAs per SM -- of different groups, so that one group's barrier waits are filled by the others);  KIND 1: 32 lanes x 8 rows.
+template <int KIND>
+__global__ void __launch_bounds__(128, KIND == 0 ? 3 : 1) sfdtd_group_kernel(const __grid_constant__ KArgs A) {
+    const CtaDesc *cd = A.ctas + blockIdx.x;
+    if (KIND == 0) {
+        if (cd->cls == 0) step_body<16, 4, true>(A, cd);
+        else step_body<32, 4, true>(A, cd);
+    } else {
+        step_body<32, 8, true>(A, cd);
+    }
+}
+
+
+// ---- sfdtd_synth_controls: the curves exactly as the stepper evaluates them -----------------------------------------
+__global__ void sfdtd_synth_controls_kernel(const __grid_constant__ KArgs A, sfdtd_array f0, sfdtd_array x_b, sfdtd_array v_b,
+                                            sfdtd_array F_b, sfdtd_array u_H) {
+    const int b = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= A.a.Nt) return;
+    const int g = n + A.sy.t_0;
+    auto put = [&](const sfdtd_array &o, double v) { if (o.ptr) ((double *)o.ptr)[(int64_t)b * o.bs + (int64_t)n * o.ts] = v; };
+    put(f0, sy_f0(A.sy, b, g)); put(x_b, sy_xb(A.sy, b, g)); put(v_b, sy_vb(A.sy, b, g)); put(F_b, sy_Fb(A.sy, b, g));
+    put(u_H, sy_uH(A.sy, b, g));
+}
+
+// ---- sfdtd_postprocess: NaN / silence flags, l-infinity gain, PCM quantisation (one CTA per string) ------------------
+template <int BITS>
+__global__ void __launch_bounds__(256) sfdtd_postprocess_kernel(sfdtd_array U, sfdtd_array Z, int n0, int ns, double silence_db,
+                                                               int normalize, uint8_t *is_nan, uint8_t *is_silent, double *gain_out,
+                                                               uint8_t *pu, uint8_t *pz, uint8_t *pw, int64_t pitch) {
+    const int b = blockIdx.x;
+    const double *u = (const double *)U.ptr + (int64_t)b * U.bs, *z = (const double *)Z.ptr + (int64_t)b * Z.bs;
+    double sq = 0.0, mx = 0.0; int nan = 0;
+    for (int n = threadIdx.x; n < ns; n += blockDim.x) {
+        const double v = u[(int64_t)(n0 + n) * U.ts];
+        nan |= (v != v); sq += v * v; mx = fmax(mx, fabs(v));
+    }
+    __shared__ double s_sq[8], s_mx[8]; __shared__ int s_nan[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(FULLMASK, sq, o); mx = fmax(mx, __shfl_xor_sync(FULLMASK, mx, o)); nan |= __shfl_xor_sync(FULLMASK, nan, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_sq[threadIdx.x >> 5] = sq; s_mx[threadIdx.x >> 5] = mx; s_nan[threadIdx.x >> 5] = nan; }
+    __syncthreads();
+    sq = 0.0; mx = 0.0; nan = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { sq += s_sq[w]; mx = fmax(mx, s_mx[w]); nan |= s_nan[w]; }
+    // a NaN string is zeroed before the silence test (simulate.py:334-335): rms 0 -> -inf dB -> silent
+    const double rms = nan ? 0.0 : sqrt(sq / (double)ns);
+    const bool silent = 20.0 * log10(rms) <= silence_db;
+    double gain = 1.0;
+    if (normalize && !nan && mx != 0.0) gain = 1.0 / mx;          // ell_infty_normalize (audio.py:42-48)
+    if (threadIdx.x == 0) {
+        if (is_nan) is_nan[b] = (uint8_t)nan;
+        if (is_silent) is_silent[b] = silent ? 1 : 0;
+        if (gain_out) gain_out[b] = gain;
+    }
+    if (!pu && !pz && !pw) return;
+    constexpr int BY = BITS / 8;
+    constexpr double SC = BITS == 16 ? 32768.0 : 8388608.0, LO = -SC, HI = SC - 1.0;
+    auto q = [&](double v) -> int { v = (v != v) ? 0.0 : v * SC; return __double2int_rn(fmin(fmax(v, LO), HI)); };
+    const int64_t row = (int64_t)b * (pitch ? pitch : (int64_t)ns * BY);
+    const bool aligned = (pitch % 4) == 0 && pitch > 0;
+    // four samples per thread and pass: 4 * BY bytes = BY 32-bit words when the rows are word aligned
+    for (int n4 = threadIdx.x * 4; n4 < ns; n4 += blockDim.x * 4) {
+        int qu[4], qz[4], qw[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int n = n4 + c;
+            double uv = 0.0, zv = 0.0;
+            if (n < ns) { uv = u[(int64_t)(n0 + n) * U.ts]; zv = z[(int64_t)(n0 + n) * Z.ts]; }
+            qu[c] = q(gain * uv); qz[c] = q(gain * zv); qw[c] = q(gain * uv + gain * zv);
+        }
+        auto store = [&](uint8_t *base, const int (&v)[4]) {
+            if (!base) return;
+            uint8_t *o = base + row + (int64_t)n4 * BY;
+            if (aligned && n4 + 4 <= ns) {
+                uint32_t *w = (uint32_t *)o;
+                if (BITS == 16) {
+                    w[0] = (uint32_t)(v[0] & 0xffff) | ((uint32_t)v[1] << 16); w[1] = (uint32_t)(v[2] & 0xffff) | ((uint32_t)v[3] << 16);
+                } else {
+                    const uint32_t a = (uint32_t)v[0] & 0xffffffu, bq = (uint32_t)v[1] & 0xffffffu, c = (uint32_t)v[2] & 0xffffffu, d = (uint32_t)v[3] & 0xffffffu;
+                    w[0] = a | (bq << 24); w[1] = (bq >> 8) | (c << 16); w[2] = (c >> 16) | (d << 8);
+                }
+            } else {
+                for (int c = 0; c < 4 && n4 + c < ns; c++)
+                    for (int k = 0; k < BY; k++) o[c * BY + k] = (uint8_t)((uint32_t)v[c] >> (8 * k));
+            }
+        };
+        store(pu, qu); store(pz, qz); store(pw, qw);
+    }
+}
 
 // ---- FMA-pipe peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has no FP64/FP32 FMA figure) ----
 template <typename T>
@@ -1318,25 +1583,25 @@ __global__ void __launch_bounds__(256) sfdtd_fma_peak_kernel(T *out, int iters, 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 
-struct Config { int L, ET, maxt; bool grouped; int tier; void (*kern)(const KArgs); };
-#define CFG_I(L_, ET_, MB_, TIER_) Config{L_, ET_, 128, false, TIER_, sfdtd_step_kernel<L_, ET_, false, 128, MB_>}
-#define CFG_G(L_, ET_, MT_) Config{L_, ET_, MT_, true, 0, sfdtd_step_kernel<L_, ET_, true, MT_, 1>}
-// smallest first.  independent mode: <=128-thread CTAs, a string needs rows <= L*ET; tier = register budget variant
+// independent-mode kernels: <=128-thread CTAs, a string needs rows <= L*ET; tier = kernel set
 // (tier 2, the default: 16 lanes x 4 rows for every string up to 64 rows, then 32x4, 32x8 -- measured fastest; tier 0 also
 // uses the 8-lane kernels, for A/B runs via SFDTD_TIER=0; 2- and 3-row kernels, tighter register caps (128) and a
 // REDUX-based max reduction all measured slower).
-// grouped mode: one CTA per group, needs rows <= L*ET and ceil32(G*L) <= maxt.
-const Config g_configs[] = {
+struct Config { int L, ET, tier; void (*kern)(const KArgs); };
+#define CFG_I(L_, ET_, MB_, TIER_) Config{L_, ET_, TIER_, sfdtd_step_kernel<L_, ET_, 128, MB_>}
+const Config g_configs[] = {   // smallest first
     CFG_I(8, 4, 3, 0), CFG_I(8, 6, 2, 0), CFG_I(16, 4, 3, 0), CFG_I(16, 6, 2, 0), CFG_I(32, 4, 3, 0), CFG_I(32, 8, 1, 0),
     CFG_I(16, 4, 3, 2), CFG_I(32, 4, 3, 2), CFG_I(32, 8, 1, 2),
     CFG_I(8, 4, 3, 3), CFG_I(16, 4, 3, 3), CFG_I(32, 4, 3, 3), CFG_I(32, 8, 1, 3),
-    CFG_G(8, 4, 256), CFG_G(8, 6, 256), CFG_G(16, 4, 384), CFG_G(16, 4, 512), CFG_G(16, 6, 384), CFG_G(32, 4, 1024), CFG_G(32, 8, 128), CFG_G(32, 8, 512),
 };
 #ifndef SFDTD_DEFAULT_TIER
 #define SFDTD_DEFAULT_TIER 2
 #endif
-constexpr int DEFAULT_TIER = SFDTD_DEFAULT_TIER;
 constexpr int N_CONFIGS = sizeof(g_configs) / sizeof(g_configs[0]);
+// grouped-mode kernels and the slot shapes of their CTA classes
+void (*const g_group_kernels[2])(const KArgs) = {sfdtd_group_kernel<0>, sfdtd_group_kernel<1>};
+struct GShape { int L, ET; };
+const GShape g_gshape[2][2] = {{{16, 4}, {32, 4}}, {{32, 8}, {32, 8}}};
 
 // longitudinal allocation classes of the independent mode (rows incl. the two guards)
 int wl_class(int rows, int c_min = 16) {
@@ -1344,46 +1609,106 @@ int wl_class(int rows, int c_min = 16) {
     while (c < rows) c *= 2;
     return c;
 }
-
 size_t xax_doubles(int NXT, bool need_xax) { return need_xax ? (size_t)((NXT + 3) / 4) * 2 : 0; }
-
 // independent mode: nslots strings with WLp longitudinal rows each
 size_t smem_bytes_indep(const Config &c, int nslots, int NXT, int WLp, bool need_xax) {
     const size_t dbl = xax_doubles(NXT, need_xax) + (size_t)nslots * (slot_fixed_doubles(c.L, c.ET, false) + slot_long_doubles(WLp, false, c.L));
     return dbl * sizeof(double) + 16;
 }
-
-int kernel_regs(const Config &c) {
+int kernel_regs(void (*kern)(const KArgs)) {
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, c.kern) != cudaSuccess) { cudaGetLastError(); return 255; }
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return 255; }
     return fa.numRegs;
 }
+int env_int(const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; }
+double env_dbl(const char *name, double dflt) { const char *v = getenv(name); return v ? atof(v) : dflt; }
 
-// grow-only device scratch (per device), so that a call does not pay cudaMalloc / cudaFree (both synchronise the device)
-struct Scratch { void *p = nullptr; size_t cap = 0; };
-std::map<std::pair<int, int>, Scratch> g_scratch;      // (device, slot) -> buffer
-cudaError_t scratch_get(int dev, int slot, size_t bytes, void **out) {
-    Scratch &sc = g_scratch[{dev, slot}];
-    if (sc.cap < bytes) {
-        if (sc.p) { cudaError_t e = cudaFree(sc.p); if (e != cudaSuccess) return e; sc.p = nullptr; sc.cap = 0; }
-        const size_t cap = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&sc.p, cap);
-        if (e != cudaSuccess) return e;
-        sc.cap = cap;
-    }
-    *out = sc.p;
-    return cudaSuccess;
-}
-
-// side streams so that the launches of different buckets overlap
-std::mutex g_stream_mu;
-std::vector<cudaStream_t> g_side_streams;
-std::vector<cudaEvent_t> g_side_events;
-cudaEvent_t g_fork_event = nullptr;
+// side streams (per device) so that the launches of different buckets overlap; shared by all plans of the device
+std::mutex g_mu;
+std::map<int, std::vector<cudaStream_t>> g_side_streams;
+std::map<int, bool> g_pool_ready;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "%s: %s", #x, cudaGetErrorString(e_)); rc = SFDTD_ERR_CUDA; goto done; } } while (0)
 
+struct Launch {
+    bool grouped = false;
+    int cfg = 0;                    // independent: index into g_configs; grouped: kernel kind
+    int grid = 0, threads = 0, cluster = 1, WLp = 0, n_items = 0;
+    size_t smem = 0, off = 0;       // off: first entry of ids (independent) / of ctas (grouped)
+    bool need_xax = false;
+    bool queue = false; int q_slice = 0, q_nslices = 0, q_full = 0; size_t q_idx = 0, done_off = 0;
+};
+
+int validate(const sfdtd_args *args) {
+    if (!args) { snprintf(g_err, sizeof g_err, "args is NULL"); return SFDTD_ERR_ARG; }
+    const sfdtd_args &a = *args;
+    if (a.abi_version != SFDTD_ABI_VERSION) { snprintf(g_err, sizeof g_err, "abi_version %d != %d", a.abi_version, SFDTD_ABI_VERSION); return SFDTD_ERR_ARG; }
+    if (a.dtype != SFDTD_F64) { snprintf(g_err, sizeof g_err, "only SFDTD_F64 is built"); return SFDTD_ERR_UNSUPPORTED; }
+    if (a.B <= 0 || a.group_size <= 0 || a.Nt < 0 || a.Nx_t1 <= 0 || a.Nx_l1 <= 0) { snprintf(g_err, sizeof g_err, "bad sizes"); return SFDTD_ERR_ARG; }
+    const void *req[] = {a.state_u.ptr, a.state_z.ptr, a.kappa.ptr, a.alpha.ptr, a.pos.ptr, a.T60.ptr, a.phi_0.ptr, a.phi_1.ptr,
+                         a.x_H.ptr, a.w_H.ptr, a.M_r.ptr, a.alpha_H.ptr, a.bow_mask, a.hammer_mask, a.xax, a.uout.ptr, a.zout.ptr,
+                         a.sig0, a.sig1};
+    for (const void *p : req) if (!p) { snprintf(g_err, sizeof g_err, "a required pointer is NULL"); return SFDTD_ERR_ARG; }
+    if (a.synth) {
+        const sfdtd_synth &y = *a.synth;
+        const void *rq[] = {y.f0_a, y.f0_b, y.mod_frq, y.mod_amp, y.vib_t0, y.x_b1, y.x_b2, y.v_b1, y.v_b2, y.F_b1, y.F_b2, y.pulloff, y.wid, y.v_H};
+        for (const void *p : rq) if (!p) { snprintf(g_err, sizeof g_err, "a pointer of sfdtd_synth is NULL"); return SFDTD_ERR_ARG; }
+        if (y.Nt_full <= 0 || !(y.sr > 0)) { snprintf(g_err, sizeof g_err, "bad sfdtd_synth sizes"); return SFDTD_ERR_ARG; }
+    } else {
+        const void *rq[] = {a.f0.ptr, a.x_b.ptr, a.v_b.ptr, a.F_b.ptr, a.wid.ptr, a.u_H.ptr};
+        for (const void *p : rq) if (!p) { snprintf(g_err, sizeof g_err, "a required pointer is NULL"); return SFDTD_ERR_ARG; }
+    }
+    if ((a.flags & SFDTD_MANUFACTURED) && !a.p_a.ptr) { snprintf(g_err, sizeof g_err, "p_a is NULL"); return SFDTD_ERR_ARG; }
+    return SFDTD_OK;
+}
+
+void fill_kargs(KArgs &K, const sfdtd_args &a) {
+    memset(&K, 0, sizeof K);
+    K.a = a;
+    if (a.synth) { K.sy = *a.synth; K.has_synth = 1; }
+    K.a.synth = nullptr;
+    K.k = (double)a.k; K.ik = 1.0 / (double)a.k; K.k2 = pow((double)a.k, 2.); K.k4 = pow((double)a.k, 4.);
+    K.th = (double)a.theta_t;
+    { const float om = 1 - a.theta_t; K.omth = (double)om; }                 // float32 (string.cpp:148)
+    { const float t1 = 2 * a.theta_t - 1; const float t2 = 2 * t1; K.tt1 = (double)t1; K.tt2 = (double)t2; }   // string.cpp:30-31
+    K.lamc = (double)a.lambda_c; K.order = (double)a.relative_order;
+    K.mhd = (double)(-0.01f);                                                // hammer.cpp:3
+    K.max_iter = a.max_iter > 0 ? a.max_iter : 100;
+}
+
+// the device the call's memory lives on becomes the current device for the duration of the call
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    cudaError_t enter(const void *ptr) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != prev) {
+            e = cudaSetDevice(at.device);
+            if (e != cudaSuccess) return e;
+            switched = true;
+        } else cudaGetLastError();
+        return cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 }  // namespace
+
+struct sfdtd_plan {
+    int dev = 0, n_sms = 0;
+    int32_t B = 0, group_size = 0, Nt = 0, Nx_t1 = 0, Nx_l1 = 0, n_groups = 0;
+    uint32_t flags = 0;
+    std::vector<Launch> launches;
+    char *block = nullptr;           // one device allocation: maxNl | ids | ctas | queue words | width table | u_H carry
+    int32_t *d_maxNl = nullptr, *d_ids = nullptr, *d_queue = nullptr, *d_wtab = nullptr;
+    CtaDesc *d_ctas = nullptr;
+    double *d_uH = nullptr;
+    size_t queue_words = 0, n_buckets = 0;
+    cudaEvent_t fork = nullptr;
+    std::vector<cudaEvent_t> joins;
+    bool verbose = false;
+};
 
 extern "C" const char *sfdtd_last_error(void) { return g_err; }
 extern "C" int sfdtd_abi_version(void) { return SFDTD_ABI_VERSION; }
@@ -1419,268 +1744,414 @@ done:
     return rc;
 }
 
-extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
+extern "C" int sfdtd_plan_destroy(sfdtd_plan *plan, void *cuda_stream) {
+    if (!plan) return SFDTD_OK;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != plan->dev) cudaSetDevice(plan->dev);
+    if (plan->block) cudaFreeAsync(plan->block, (cudaStream_t)cuda_stream);
+    if (plan->fork) cudaEventDestroy(plan->fork);
+    for (cudaEvent_t e : plan->joins) cudaEventDestroy(e);
+    if (prev != plan->dev && prev >= 0) cudaSetDevice(prev);
+    delete plan;
+    return SFDTD_OK;
+}
+
+extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdtd_plan **out) {
     g_err[0] = 0;
-    if (!args) { snprintf(g_err, sizeof g_err, "args is NULL"); return SFDTD_ERR_ARG; }
+    if (!out) { snprintf(g_err, sizeof g_err, "plan pointer is NULL"); return SFDTD_ERR_ARG; }
+    *out = nullptr;
+    { const int v = validate(args); if (v != SFDTD_OK) return v; }
     const sfdtd_args &a = *args;
-    if (a.abi_version != SFDTD_ABI_VERSION) { snprintf(g_err, sizeof g_err, "abi_version %d != %d", a.abi_version, SFDTD_ABI_VERSION); return SFDTD_ERR_ARG; }
-    if (a.dtype != SFDTD_F64) { snprintf(g_err, sizeof g_err, "only SFDTD_F64 is built"); return SFDTD_ERR_UNSUPPORTED; }
-    if (a.B <= 0 || a.group_size <= 0 || a.Nt < 0 || a.Nx_t1 <= 0 || a.Nx_l1 <= 0) { snprintf(g_err, sizeof g_err, "bad sizes"); return SFDTD_ERR_ARG; }
-    const void *req[] = {a.state_u.ptr, a.state_z.ptr, a.kappa.ptr, a.alpha.ptr, a.f0.ptr, a.pos.ptr, a.T60.ptr, a.x_b.ptr, a.v_b.ptr,
-                         a.F_b.ptr, a.wid.ptr, a.phi_0.ptr, a.phi_1.ptr, a.x_H.ptr, a.w_H.ptr, a.M_r.ptr, a.alpha_H.ptr, a.u_H.ptr,
-                         a.bow_mask, a.hammer_mask, a.xax, a.uout.ptr, a.zout.ptr, a.v_r.ptr, a.F_H.ptr, a.u_H_out.ptr, a.sig0, a.sig1};
-    for (const void *p : req) if (!p) { snprintf(g_err, sizeof g_err, "a required pointer is NULL"); return SFDTD_ERR_ARG; }
-    if (a.Nt <= 2) return SFDTD_OK;
-
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    const auto t_host0 = std::chrono::steady_clock::now();
-    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count(); };
-    double t_pre = 0, t_launch = 0;
-    int rc = SFDTD_OK, dev = 0;
-    bool locked = false;
+    int rc = SFDTD_OK;
+    DeviceGuard guard;
+    sfdtd_plan *P = new sfdtd_plan();
+    int32_t *d_max = nullptr; float *d_est = nullptr;
     const int n_groups = (a.B + a.group_size - 1) / a.group_size;
-    int32_t *d_max = nullptr, *d_ids = nullptr, *d_wtab = nullptr, *d_queue = nullptr, *d_done = nullptr;
-    int n_sms = 0;
-    size_t q_off = 0;
-    // smallest longitudinal allocation class: a coarser one merges buckets (one work queue balances more strings) for more
-    // shared memory per string
-    const int wl_min = getenv("SFDTD_WLMIN") ? std::max(16, atoi(getenv("SFDTD_WLMIN"))) : SFDTD_DEFAULT_WLMIN;
-    // longitudinal rows per lane that still count as a short loop (lanes >= allocation class / lane_div)
-    const int lane_div = getenv("SFDTD_LANE_DIV") ? std::max(1, atoi(getenv("SFDTD_LANE_DIV"))) : SFDTD_DEFAULT_LANE_DIV;
-    const bool use_queue = getenv("SFDTD_QUEUE") ? atoi(getenv("SFDTD_QUEUE")) != 0 : SFDTD_DEFAULT_QUEUE;
-    float *d_est = nullptr;
     std::vector<float> h_est(a.B);
-    std::vector<int32_t> h_max(2 * (size_t)a.B);
+    std::vector<int32_t> h_max(2 * (size_t)a.B), h_ids;
     std::vector<uint8_t> h_bow(a.B), h_ham(a.B);
-    struct Bucket { std::vector<int32_t> ids; size_t smem = 0, off = 0; };
-    std::map<std::pair<int, int>, Bucket> buckets;      // (config index, WLp) -> items
-    std::vector<int32_t> h_ids;
-    size_t n_ids_total = 0;
-    struct TimedBucket { int cfg, WLp, items, threads, grid; cudaEvent_t e0, e1; };
-    std::vector<TimedBucket> timed;
-    const bool verbose = getenv("SFDTD_VERBOSE") != nullptr;
+    std::vector<CtaDesc> h_ctas;
+    // run-time knobs (read once per plan)
+    // smallest longitudinal allocation class: a coarser one merges buckets (one work queue balances more strings) for more
+    // shared memory per string; lane_div: longitudinal rows per lane that still count as a short loop
+    const int wl_min = std::max(16, env_int("SFDTD_WLMIN", SFDTD_DEFAULT_WLMIN));
+    const int lane_div = std::max(1, env_int("SFDTD_LANE_DIV", SFDTD_DEFAULT_LANE_DIV));
+    const int min_lanes_env = env_int("SFDTD_MIN_LANES", 0);
+    const bool use_queue = env_int("SFDTD_QUEUE", SFDTD_DEFAULT_QUEUE) != 0;
+    const int tier = std::min(3, std::max(0, env_int("SFDTD_TIER", SFDTD_DEFAULT_TIER)));
+    const int th_force = env_int("SFDTD_CTA_THREADS", 0);
+    const int pad_smem = env_int("SFDTD_PAD_SMEM", 0);
+    const int q_want = env_int("SFDTD_QSLICES", 8);
+    const double tail_rounds = env_dbl("SFDTD_QTAIL", 1.0), min_rounds = env_dbl("SFDTD_QMIN", 2.0);
     const bool skip_aux = a.flags & SFDTD_SKIP_AUX;
-    const int tier = getenv("SFDTD_TIER") ? std::min(3, std::max(0, atoi(getenv("SFDTD_TIER")))) : DEFAULT_TIER;
-
+    const bool manuf = a.flags & SFDTD_MANUFACTURED;
+    struct IBucket { std::vector<int32_t> ids; };
+    struct GBucket { std::vector<CtaDesc> ctas; size_t smem = 0; };
+    std::map<std::pair<int, int>, IBucket> ib;                       // (config index, WLp) -> strings
+    std::map<std::tuple<int, int, int, int>, GBucket> gb;            // (kind, cluster size, threads, smem class) -> CTAs
     KArgs K;
-    memset(&K, 0, sizeof K);
-    K.a = a;
-    K.k = (double)a.k; K.ik = 1.0 / (double)a.k; K.k2 = pow((double)a.k, 2.); K.k4 = pow((double)a.k, 4.);
-    K.th = (double)a.theta_t;
-    { const float om = 1 - a.theta_t; K.omth = (double)om; }                 // float32 (string.cpp:148)
-    { const float t1 = 2 * a.theta_t - 1; const float t2 = 2 * t1; K.tt1 = (double)t1; K.tt2 = (double)t2; }   // string.cpp:30-31
-    K.lamc = (double)a.lambda_c; K.order = (double)a.relative_order;
-    K.mhd = (double)(-0.01f);                                                // hammer.cpp:3
-    K.max_iter = a.max_iter > 0 ? a.max_iter : 100;
+    fill_kargs(K, a);
+    P->verbose = getenv("SFDTD_VERBOSE") != nullptr;
+    P->B = a.B; P->group_size = a.group_size; P->Nt = a.Nt; P->Nx_t1 = a.Nx_t1; P->Nx_l1 = a.Nx_l1; P->n_groups = n_groups;
+    P->flags = a.flags;
 
-    CK(cudaGetDevice(&dev));
-    g_stream_mu.lock(); locked = true;          // scratch buffers and side streams are shared by all callers
-    CK(scratch_get(dev, 0, sizeof(int32_t) * 2 * (size_t)a.B, (void **)&d_max));
-    CK(scratch_get(dev, 1, sizeof(int32_t) * (size_t)n_groups * a.Nt, (void **)&d_wtab));
-    CK(scratch_get(dev, 2, sizeof(float) * (size_t)a.B, (void **)&d_est));
+    CK(guard.enter(a.state_u.ptr));
+    CK(cudaGetDevice(&P->dev));
+    CK(cudaDeviceGetAttribute(&P->n_sms, cudaDevAttrMultiProcessorCount, P->dev));
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!g_pool_ready[P->dev]) {
+            // keep freed scratch in the device's default pool instead of returning it to the driver at every synchronisation
+            cudaMemPool_t pool; uint64_t thr = UINT64_MAX;
+            CK(cudaDeviceGetDefaultMemPool(&pool, P->dev));
+            CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+            g_pool_ready[P->dev] = true;
+        }
+    }
+    if (a.Nt <= 2) { *out = P; return SFDTD_OK; }
+
+    // ---- prepass: per-string grid maxima and difficulty estimate; ONE device->host read ----
+    CK(cudaMallocAsync((void **)&d_max, sizeof(int32_t) * 2 * (size_t)a.B, stream));
+    CK(cudaMallocAsync((void **)&d_est, sizeof(float) * (size_t)a.B, stream));
     sfdtd_prepass_kernel<<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B, d_est);
     g_launches++;
     CK(cudaGetLastError());
-    sfdtd_width_kernel<<<dim3((a.Nt + 127) / 128, n_groups), 128, 0, stream>>>(K, d_wtab);
-    g_launches++;
-    CK(cudaGetLastError());
-    K.Wtab = d_wtab; K.maxNl = d_max + a.B;
     CK(cudaMemcpyAsync(h_max.data(), d_max, sizeof(int32_t) * 2 * (size_t)a.B, cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(h_est.data(), d_est, sizeof(float) * (size_t)a.B, cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(h_bow.data(), a.bow_mask, a.B, cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(h_ham.data(), a.hammer_mask, a.B, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    t_pre = host_ms();
 
+    // ---- bucketing ----
     for (int g = 0; g < n_groups; g++) {
         const int g0 = g * a.group_size, G = std::min(a.group_size, a.B - g0);
-        bool forced = false;
-        int Wt = 0, rows_g = 0;
+        bool forced = manuf;
+        int Wt = 0;
         for (int s = 0; s < G; s++) {
-            forced = forced || h_bow[g0 + s] || h_ham[g0 + s] || (a.flags & SFDTD_MANUFACTURED);
+            forced = forced || h_bow[g0 + s] || h_ham[g0 + s];
             Wt = std::max(Wt, h_max[g0 + s] + 1);
         }
-        for (int s = 0; s < G; s++) {
-            // rows a string can need: its own N_t + 3 (+ the bow window of a bowed string), never more than W_t
-            const int rows = std::min(Wt, h_max[g0 + s] + 3 + (h_bow[g0 + s] ? 8 : 0));
-            if (!forced) {
-                // lanes: enough rows for the transverse block, and enough lanes that the longitudinal loops stay short
-                const int wlc = wl_class(long_rows(h_max[a.B + g0 + s]));       // lanes follow the string's own size ...
-                const int min_lanes = std::max(std::min(32, wlc / lane_div), getenv("SFDTD_MIN_LANES") ? atoi(getenv("SFDTD_MIN_LANES")) : 0);
+        // rows a string can need: its own N_t + 3 (+ the bow window of a bowed string), never more than W_t;
+        // every padded row is forced in the manufactured mode (string.cpp:227-232)
+        auto rows_of = [&](int b) { return manuf ? Wt : std::min(Wt, h_max[b] + 3 + (h_bow[b] ? 8 : 0)); };
+        // lanes that keep the longitudinal loops short
+        auto lanes_of = [&](int b) { return std::max(std::min(32, wl_class(long_rows(h_max[a.B + b])) / lane_div), min_lanes_env); };
+        if (!forced) {
+            for (int s = 0; s < G; s++) {
+                const int b = g0 + s, rows = rows_of(b), min_lanes = lanes_of(b);
                 int pick = -1;
                 for (int c = 0; c < N_CONFIGS && pick < 0; c++)
-                    if (!g_configs[c].grouped && g_configs[c].tier == tier && rows <= g_configs[c].L * g_configs[c].ET &&
-                        g_configs[c].L >= min_lanes) pick = c;
+                    if (g_configs[c].tier == tier && rows <= g_configs[c].L * g_configs[c].ET && g_configs[c].L >= min_lanes) pick = c;
                 if (pick < 0) {
-                    snprintf(g_err, sizeof g_err, "string %d: %d transverse rows are outside the built kernel set", g0 + s, rows);
+                    snprintf(g_err, sizeof g_err, "string %d: %d transverse rows are outside the built kernel set", b, rows);
                     rc = SFDTD_ERR_UNSUPPORTED; goto done;
                 }
-                buckets[{pick, wl_class(long_rows(h_max[a.B + g0 + s]), wl_min)}].ids.push_back(g0 + s);   // ... the allocation class may be coarser
+                ib[{pick, wl_class(long_rows(h_max[a.B + b]), wl_min)}].ids.push_back(b);   // the allocation class may be coarser than the lane class
             }
-            rows_g = std::max(rows_g, rows);
+            continue;
         }
-        if (forced) {
-            int pick = -1;
-            for (int c = 0; c < N_CONFIGS && pick < 0; c++) {
-                const Config &cf = g_configs[c];
-                const int threads = (a.group_size * cf.L + 31) / 32 * 32;
-                if (cf.grouped && rows_g <= cf.L * cf.ET && threads <= cf.maxt) pick = c;
-            }
-            if (pick < 0) {
-                snprintf(g_err, sizeof g_err, "group %d: %d transverse rows with %d strings is outside the built kernel set", g, rows_g, G);
+        // forced group: one cluster; small strings on 16 lanes (8 per CTA), large ones on 32 lanes (4 per CTA)
+        if (G > GB_MAX) {
+            snprintf(g_err, sizeof g_err, "group %d: %d strings with bowed / hammered ones (grouped mode holds <= %d per group)", g, G, GB_MAX);
+            rc = SFDTD_ERR_UNSUPPORTED; goto done;
+        }
+        int kind = 0;
+        std::vector<int> cls(G);
+        for (int s = 0; s < G; s++) {
+            const int rows = rows_of(g0 + s);
+            if (rows > 256) {
+                snprintf(g_err, sizeof g_err, "string %d: %d transverse rows are outside the built kernel set", g0 + s, rows);
                 rc = SFDTD_ERR_UNSUPPORTED; goto done;
             }
-            // shared memory of this group's CTA: fixed slots + the strings' own longitudinal blocks
-            const Config &cf = g_configs[pick];
-            const int threads = (a.group_size * cf.L + 31) / 32 * 32, nslots = threads / cf.L;
-            size_t dbl = xax_doubles(a.Nx_t1, true) + (size_t)nslots * slot_fixed_doubles(cf.L, cf.ET, true) + (size_t)(nslots + 2) / 2 + 2;
-            for (int s = 0; s < nslots; s++) dbl += slot_long_doubles(long_rows(h_max[a.B + g0 + std::min(s, G - 1)]), true, cf.L);
-            Bucket &bk = buckets[{pick, 0}];
-            bk.ids.push_back(g);
-            bk.smem = std::max(bk.smem, dbl * sizeof(double) + 16);
+            if (rows > 128) kind = 1;
+            cls[s] = (rows > 64 || lanes_of(g0 + s) > 16) ? 1 : 0;
         }
+        std::vector<CtaDesc> ctas;
+        for (int c = 0; c < 2; c++) {
+            const int per = (kind == 1) ? 4 : (c == 0 ? 8 : 4);
+            CtaDesc cd; memset(&cd, 0, sizeof cd);
+            cd.group = g; cd.cls = (kind == 1) ? 0 : c; cd.G = G;
+            for (int s = 0; s < G; s++) {
+                if (kind == 0 && cls[s] != c) continue;
+                if (kind == 1 && c == 1) continue;
+                cd.str[cd.n] = g0 + s; cd.gidx[cd.n] = s; cd.n++;
+                if (cd.n == per) { ctas.push_back(cd); cd.n = 0; }
+            }
+            if (cd.n) ctas.push_back(cd);
+        }
+        const int CS = (int)ctas.size();
+        if (CS > 8) {
+            snprintf(g_err, sizeof g_err, "group %d: needs %d CTAs (a cluster holds <= 8)", g, CS);
+            rc = SFDTD_ERR_UNSUPPORTED; goto done;
+        }
+        int threads = 128;
+        if (CS == 1) { const GShape sh = g_gshape[kind][ctas[0].cls]; threads = std::min(128, (ctas[0].n * sh.L + 31) / 32 * 32); }
+        size_t smem = 0;
+        for (const CtaDesc &cd : ctas) {
+            const GShape sh = g_gshape[kind][cd.cls];
+            const int nslots = threads / sh.L;
+            size_t dbl = GB_DOUBLES + xax_doubles(a.Nx_t1, true) + (size_t)nslots * slot_fixed_doubles(sh.L, sh.ET, true) + (size_t)(nslots + 2) / 2 + 2;
+            for (int s = 0; s < nslots; s++) dbl += slot_long_doubles(long_rows(h_max[a.B + cd.str[std::min(s, cd.n - 1)]]), true, sh.L);
+            smem = std::max(smem, dbl * sizeof(double) + 16);
+        }
+        if (smem > 227 * 1024) {
+            snprintf(g_err, sizeof g_err, "group %d needs %zu bytes of shared memory per CTA (> 227 KB)", g, smem);
+            rc = SFDTD_ERR_UNSUPPORTED; goto done;
+        }
+        // shared-memory class: the CTAs of a launch share one dynamic size, so a group with a few huge longitudinal grids
+        // must not cost every other group its occupancy (3 CTAs per SM up to 74 KB, 2 up to 112 KB)
+        const int sclass = smem <= 74 * 1024 ? 0 : (smem <= 112 * 1024 ? 1 : 2);
+        GBucket &bk = gb[std::make_tuple(kind, CS, threads, sclass)];
+        bk.ctas.insert(bk.ctas.end(), ctas.begin(), ctas.end());
+        bk.smem = std::max(bk.smem, smem);
     }
-    for (auto &kv : buckets) {
-        kv.second.off = n_ids_total; n_ids_total += kv.second.ids.size();
-        // independent mode: strings of similar nonlinearity share a warp (they converge in about the same number of sweeps)
-        if (!g_configs[kv.first.first].grouped)
-            std::stable_sort(kv.second.ids.begin(), kv.second.ids.end(), [&](int32_t x, int32_t y) {
-                const float ex = h_est[x], ey = h_est[y];
-                return (ex == ex ? ex : INFINITY) > (ey == ey ? ey : INFINITY);      // hardest first (they also run longest)
-            });
-        h_ids.insert(h_ids.end(), kv.second.ids.begin(), kv.second.ids.end());
-    }
-    CK(scratch_get(dev, 3, sizeof(int32_t) * h_ids.size(), (void **)&d_ids));
-    CK(cudaMemcpyAsync(d_ids, h_ids.data(), sizeof(int32_t) * h_ids.size(), cudaMemcpyHostToDevice, stream));
+
+    // ---- launches: independent buckets (smallest first: every CTA lives for the whole time loop, so a small bucket
+    // started late would trail the bulk on a nearly empty GPU), then the grouped ones ----
     {
-        const size_t nb = buckets.size();
-        while (g_side_streams.size() < nb) {
-            cudaStream_t s; cudaEvent_t e;
-            CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            g_side_streams.push_back(s); g_side_events.push_back(e);
-        }
-        if (!g_fork_event) CK(cudaEventCreateWithFlags(&g_fork_event, cudaEventDisableTiming));
-        if (use_queue) {
-            // counters: one per bucket, then one "slices done" word per set of strings (<= one per string)
-            CK(scratch_get(dev, 4, sizeof(int32_t) * (nb + (size_t)a.B + nb), (void **)&d_queue));
-            CK(cudaMemsetAsync(d_queue, 0, sizeof(int32_t) * (nb + (size_t)a.B + nb), stream));
-            d_done = d_queue + nb;
-            CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-        }
-        CK(cudaEventRecord(g_fork_event, stream));
-        // launch order: smallest buckets first.  Every CTA lives for the whole time loop, so a small bucket started late
-        // would trail the bulk by a full CTA lifetime on a nearly empty GPU; started first it overlaps with the bulk.
-        typedef std::pair<const std::pair<int, int>, Bucket> BK;
-        std::vector<BK *> order;
-        for (auto &kv : buckets) order.push_back(&kv);
-        std::stable_sort(order.begin(), order.end(), [&](const BK *x, const BK *y) {
-            const Config &cx = g_configs[x->first.first], &cy = g_configs[y->first.first];
-            (void)cx; (void)cy;
-            return x->second.ids.size() < y->second.ids.size();
-        });
-        // Optional time slices (SFDTD_SLICE=steps): every bucket advances slice by slice on its own stream, state carried
-        // through global memory.  Measured slower than one launch per bucket (each bucket pays its own tail per slice), so
-        // it is off by default; it is kept because it exercises the in-call state carry.
-        const int slice = getenv("SFDTD_SLICE") ? std::max(8, atoi(getenv("SFDTD_SLICE"))) : (1 << 30);
-        const int n_slices = (int)std::max<int64_t>(1, ((int64_t)a.Nt - 2 + slice - 1) / slice);
-        for (int si = 0; si < n_slices; si++) {
-        K.n_lo = (int32_t)(2 + (int64_t)si * slice); K.n_hi = (int32_t)std::min<int64_t>(a.Nt, 2 + ((int64_t)si + 1) * slice);
-        int bi = 0;
-        for (BK *pkv : order) {
-            BK &kv = *pkv;
-            const Config &cf = g_configs[kv.first.first];
-            const int WLp = kv.first.second;
-            const int n_items = (int)kv.second.ids.size();
-            const size_t off = kv.second.off;
-            int threads, grid;
-            size_t sm;
-            const bool need_xax = !skip_aux || cf.grouped;
-            if (cf.grouped) { threads = (a.group_size * cf.L + 31) / 32 * 32; grid = n_items; sm = kv.second.smem; }
-            else {
-                // CTA size that keeps the most strings resident per SM (registers and shared memory both bound it)
-                const int regs = kernel_regs(cf);
-                int best = 32; long best_res = -1;
-                const int th_force = getenv("SFDTD_CTA_THREADS") ? atoi(getenv("SFDTD_CTA_THREADS")) : 0;
-                for (int th : {128, 96, 64, 32}) {
-                    if (th % cf.L) continue;
-                    if (th_force && th != std::max(th_force, cf.L)) continue;
-                    const size_t b_ = smem_bytes_indep(cf, th / cf.L, a.Nx_t1, WLp, need_xax);
-                    if (b_ > 227 * 1024) continue;
-                    const long by_smem = (long)((227 * 1024) / (b_ + 1024)), by_regs = 65536 / ((long)regs * th);
-                    long res = std::min(std::min(by_smem, by_regs), 32L) * th;
-                    if (b_ > 76 * 1024 && th > 32) res /= 2;      // large CTAs cannot share an SM with other buckets: prefer smaller ones
-                    if (res > best_res) { best_res = res; best = th; }
-                }
-                threads = best;
-                const int per = threads / cf.L; grid = (n_items + per - 1) / per;
-                sm = smem_bytes_indep(cf, threads / cf.L, a.Nx_t1, WLp, need_xax);
+        typedef std::pair<const std::pair<int, int>, IBucket> IB;
+        std::vector<IB *> order;
+        for (auto &kv : ib) order.push_back(&kv);
+        std::stable_sort(order.begin(), order.end(), [](const IB *x, const IB *y) { return x->second.ids.size() < y->second.ids.size(); });
+        for (IB *pkv : order) {
+            const Config &cf = g_configs[pkv->first.first];
+            std::vector<int32_t> &ids = pkv->second.ids;
+            // strings of similar nonlinearity share a warp (they converge in about the same number of sweeps); hardest first
+            std::stable_sort(ids.begin(), ids.end(), [&](int32_t x, int32_t y) {
+                const float ex = h_est[x], ey = h_est[y];
+                return (ex == ex ? ex : INFINITY) > (ey == ey ? ey : INFINITY);
+            });
+            Launch ln;
+            ln.cfg = pkv->first.first; ln.WLp = pkv->first.second; ln.n_items = (int)ids.size(); ln.off = h_ids.size();
+            ln.need_xax = !skip_aux;
+            h_ids.insert(h_ids.end(), ids.begin(), ids.end());
+            // CTA size that keeps the most strings resident per SM (registers and shared memory both bound it)
+            const int regs = kernel_regs(cf.kern);
+            int best = 32; long best_res = -1;
+            for (int th : {128, 96, 64, 32}) {
+                if (th % cf.L) continue;
+                if (th_force && th != std::max(th_force, cf.L)) continue;
+                const size_t b_ = smem_bytes_indep(cf, th / cf.L, a.Nx_t1, ln.WLp, ln.need_xax);
+                if (b_ > 227 * 1024) continue;
+                const long by_smem = (long)((227 * 1024) / (b_ + 1024)), by_regs = 65536 / ((long)regs * th);
+                long res = std::min(std::min(by_smem, by_regs), 32L) * th;
+                if (b_ > 76 * 1024 && th > 32) res /= 2;      // large CTAs cannot share an SM with other buckets: prefer smaller ones
+                if (res > best_res) { best_res = res; best = th; }
             }
-            if (getenv("SFDTD_PAD_SMEM")) sm = std::max(sm, (size_t)atoi(getenv("SFDTD_PAD_SMEM")));    // occupancy experiments
-            if (sm > 227 * 1024) {
-                snprintf(g_err, sizeof g_err, "a bucket (L=%d, ET=%d, %s) needs %zu bytes of shared memory (> 227 KB)", cf.L, cf.ET, cf.grouped ? "grouped" : "independent", sm);
+            ln.threads = best;
+            const int per = ln.threads / cf.L;
+            ln.grid = (ln.n_items + per - 1) / per;
+            ln.smem = std::max(smem_bytes_indep(cf, per, a.Nx_t1, ln.WLp, ln.need_xax), (size_t)pad_smem);
+            if (ln.smem > 227 * 1024) {
+                snprintf(g_err, sizeof g_err, "a bucket (L=%d, ET=%d) needs %zu bytes of shared memory (> 227 KB)", cf.L, cf.ET, ln.smem);
                 rc = SFDTD_ERR_UNSUPPORTED; goto done;
             }
-            if (getenv("SFDTD_VERBOSE"))
-                fprintf(stderr, "[sfdtd] bucket L=%d ET=%d %s WLp=%d items=%d threads=%d grid=%d smem=%zu regs=%d\n", cf.L, cf.ET,
-                        cf.grouped ? "grouped" : "indep", WLp, n_items, threads, grid, sm, kernel_regs(cf));
-            CK(cudaFuncSetAttribute(cf.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(cf.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             // one shared-memory carve-out for every bucket kernel, so that CTAs of different buckets can share an SM
             CK(cudaFuncSetAttribute(cf.kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-            K.ids = d_ids + off; K.n_items = n_items; K.WLp = WLp; K.need_xax = need_xax ? 1 : 0;
-            K.queue = nullptr;
-            if (use_queue && !cf.grouped && n_slices == 1) {
+            if (use_queue) {
                 // persistent grid: what is resident at once; the warps pull their string sets from the bucket's counter
                 int per_sm = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf.kern, threads, sm));
-                const int spw = 32 / cf.L, n_sets = (n_items + spw - 1) / spw, wpc = threads / 32;
-                const int resident = std::max(1, per_sm) * n_sms;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf.kern, ln.threads, ln.smem));
+                const int spw = 32 / cf.L, n_sets = (ln.n_items + spw - 1) / spw, wpc = ln.threads / 32;
+                const int resident = std::max(1, per_sm) * P->n_sms;
                 // tail group: the sets that would run in the last round of the resident warps, in SFDTD_QSLICES time slices
                 // (default 8); a bucket with fewer than two rounds of sets is not sliced (it ends long before the bulk does)
                 const int rw = resident * wpc;
-                const int want = getenv("SFDTD_QSLICES") ? atoi(getenv("SFDTD_QSLICES")) : 8;
-                int n_sl = std::max(1, std::min(want, (a.Nt - 2) / 512));
+                int n_sl = std::max(1, std::min(q_want, (a.Nt - 2) / 512));
                 const int q_slice = ((a.Nt - 2 + n_sl - 1) / n_sl + TBS_MAX - 1) / TBS_MAX * TBS_MAX;
                 n_sl = (a.Nt - 2 + q_slice - 1) / q_slice;
-                const double tail_rounds = getenv("SFDTD_QTAIL") ? atof(getenv("SFDTD_QTAIL")) : 1.0;
-                // (SFDTD_QMIN: rounds of sets below which a bucket is not sliced; 0 forces the sliced path for the tests)
-                const double min_rounds = getenv("SFDTD_QMIN") ? atof(getenv("SFDTD_QMIN")) : 2.0;
                 const int n_tail = (n_sl > 1 && n_sets >= min_rounds * rw) ? std::max(0, std::min(n_sets, (int)(tail_rounds * rw))) : 0;
-                grid = std::min(std::min(grid, resident), (n_sets + wpc - 1) / wpc);
-                K.q_slice = q_slice; K.q_nslices = n_sl; K.q_full = n_sets - n_tail;
-                K.queue = d_queue + bi; K.done = d_done + q_off;
-                q_off += n_sets;
+                ln.grid = std::min(std::min(ln.grid, resident), (n_sets + wpc - 1) / wpc);
+                ln.queue = true; ln.q_slice = q_slice; ln.q_nslices = n_sl; ln.q_full = n_sets - n_tail;
+                ln.q_idx = P->launches.size(); ln.done_off = P->queue_words; P->queue_words += n_sets;
             }
-            cudaStream_t s = (nb > 1) ? g_side_streams[bi] : stream;
-            if (nb > 1 && si == 0) CK(cudaStreamWaitEvent(s, g_fork_event, 0));
-            if (verbose && si == 0) {
-                TimedBucket tb; tb.cfg = kv.first.first; tb.WLp = WLp; tb.items = n_items; tb.threads = threads; tb.grid = grid;
-                CK(cudaEventCreate(&tb.e0)); CK(cudaEventCreate(&tb.e1));
-                CK(cudaEventRecord(tb.e0, s));
-                timed.push_back(tb);
-            }
-            cf.kern<<<(unsigned)grid, threads, sm, s>>>(K);
-            if (verbose && si == n_slices - 1) CK(cudaEventRecord(timed[bi].e1, s));
-            g_launches++;
-            CK(cudaGetLastError());
-            if (nb > 1 && si == n_slices - 1) { CK(cudaEventRecord(g_side_events[bi], s)); CK(cudaStreamWaitEvent(stream, g_side_events[bi], 0)); }
-            bi++;
+            if (P->verbose)
+                fprintf(stderr, "[sfdtd] bucket L=%d ET=%d indep WLp=%d items=%d threads=%d grid=%d smem=%zu regs=%d\n", cf.L, cf.ET,
+                        ln.WLp, ln.n_items, ln.threads, ln.grid, ln.smem, regs);
+            P->launches.push_back(ln);
         }
+        for (auto &kv : gb) {
+            Launch ln;
+            ln.grouped = true; ln.cfg = std::get<0>(kv.first); ln.cluster = std::get<1>(kv.first); ln.threads = std::get<2>(kv.first);
+            ln.grid = (int)kv.second.ctas.size(); ln.n_items = ln.grid / ln.cluster; ln.off = h_ctas.size(); ln.need_xax = true;
+            ln.smem = std::max(kv.second.smem, (size_t)pad_smem);
+            h_ctas.insert(h_ctas.end(), kv.second.ctas.begin(), kv.second.ctas.end());
+            CK(cudaFuncSetAttribute(g_group_kernels[ln.cfg], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CK(cudaFuncSetAttribute(g_group_kernels[ln.cfg], cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            if (P->verbose)
+                fprintf(stderr, "[sfdtd] bucket grouped kind=%d cluster=%d groups=%d threads=%d grid=%d smem=%zu regs=%d\n", ln.cfg,
+                        ln.cluster, ln.n_items, ln.threads, ln.grid, ln.smem, kernel_regs(g_group_kernels[ln.cfg]));
+            P->launches.push_back(ln);
         }
     }
-    t_launch = host_ms();
-    CK(cudaStreamSynchronize(stream));
-    if (verbose) fprintf(stderr, "[sfdtd] host: prepass+readback %.1f ms, bucketing+launch %.1f ms, total %.1f ms\n", t_pre, t_launch - t_pre, host_ms());
-    for (auto &tb : timed) {
-        float ms = 0, ms0 = 0;
-        cudaEventElapsedTime(&ms, tb.e0, tb.e1); cudaEventElapsedTime(&ms0, timed[0].e0, tb.e1);
-        const Config &cf = g_configs[tb.cfg];
-        fprintf(stderr, "[sfdtd] timing L=%d ET=%d %s WLp=%d items=%d threads=%d grid=%d: %.1f ms (ends at %.1f ms)\n", cf.L, cf.ET,
-                cf.grouped ? "grouped" : "indep", tb.WLp, tb.items, tb.threads, tb.grid, ms, ms0);
+    P->n_buckets = P->launches.size();
+    {
+        // ---- device block: maxNl | ids | ctas | queue words (one counter per launch + one per set) | width table | u_H carry ----
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t o_max = 0, o_ids = al(o_max + sizeof(int32_t) * a.B), o_cta = al(o_ids + sizeof(int32_t) * h_ids.size());
+        const size_t o_q = al(o_cta + sizeof(CtaDesc) * h_ctas.size());
+        P->queue_words += P->n_buckets;
+        const size_t o_w = al(o_q + sizeof(int32_t) * P->queue_words), o_uh = al(o_w + sizeof(int32_t) * (size_t)n_groups * a.Nt);
+        const size_t total = al(o_uh + sizeof(double) * 2 * (size_t)a.B);
+        CK(cudaMallocAsync((void **)&P->block, total, stream));
+        P->d_maxNl = (int32_t *)(P->block + o_max); P->d_ids = (int32_t *)(P->block + o_ids); P->d_ctas = (CtaDesc *)(P->block + o_cta);
+        P->d_queue = (int32_t *)(P->block + o_q); P->d_wtab = (int32_t *)(P->block + o_w); P->d_uH = (double *)(P->block + o_uh);
+        CK(cudaMemcpyAsync(P->d_maxNl, d_max + a.B, sizeof(int32_t) * a.B, cudaMemcpyDeviceToDevice, stream));
+        if (!h_ids.empty()) CK(cudaMemcpyAsync(P->d_ids, h_ids.data(), sizeof(int32_t) * h_ids.size(), cudaMemcpyHostToDevice, stream));
+        if (!h_ctas.empty()) CK(cudaMemcpyAsync(P->d_ctas, h_ctas.data(), sizeof(CtaDesc) * h_ctas.size(), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));        // the host vectors go out of scope; still before any stepper kernel is queued
+        CK(cudaEventCreateWithFlags(&P->fork, cudaEventDisableTiming));
+        for (size_t i = 0; i < P->n_buckets; i++) {
+            cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            P->joins.push_back(e);
+        }
+        std::lock_guard<std::mutex> lk(g_mu);
+        std::vector<cudaStream_t> &ss = g_side_streams[P->dev];
+        while (ss.size() < P->n_buckets) {
+            cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            ss.push_back(st);
+        }
     }
-    for (auto &tb : timed) { cudaEventDestroy(tb.e0); cudaEventDestroy(tb.e1); }
 done:
-    if (rc != SFDTD_OK) cudaDeviceSynchronize();
-    if (locked) g_stream_mu.unlock();
+    if (d_max) cudaFreeAsync(d_max, stream);
+    if (d_est) cudaFreeAsync(d_est, stream);
+    if (rc != SFDTD_OK) { sfdtd_plan_destroy(P, stream); return rc; }
+    *out = P;
+    return rc;
+}
+
+extern "C" int sfdtd_forward_plan(sfdtd_plan *P, const sfdtd_args *args, void *cuda_stream) {
+    g_err[0] = 0;
+    if (!P) { snprintf(g_err, sizeof g_err, "plan is NULL"); return SFDTD_ERR_ARG; }
+    { const int v = validate(args); if (v != SFDTD_OK) return v; }
+    const sfdtd_args &a = *args;
+    if (a.B != P->B || a.group_size != P->group_size || a.Nt != P->Nt || a.Nx_t1 != P->Nx_t1 || a.Nx_l1 != P->Nx_l1 || a.flags != P->flags) {
+        snprintf(g_err, sizeof g_err, "args do not match the plan (B, group_size, Nt, Nx_t1, Nx_l1, flags)");
+        return SFDTD_ERR_ARG;
+    }
+    if (a.Nt <= 2) return SFDTD_OK;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    int rc = SFDTD_OK;
+    DeviceGuard guard;
+    KArgs K;
+    fill_kargs(K, a);
+    std::vector<cudaEvent_t> t0, t1;
+    {
+    CK(guard.enter(a.state_u.ptr));
+    sfdtd_width_kernel<<<dim3((a.Nt + 127) / 128, P->n_groups), 128, 0, stream>>>(K, P->d_wtab);
+    g_launches++;
+    CK(cudaGetLastError());
+    K.Wtab = P->d_wtab; K.maxNl = P->d_maxNl; K.uH_carry = P->d_uH;
+    if (P->queue_words) CK(cudaMemsetAsync(P->d_queue, 0, sizeof(int32_t) * P->queue_words, stream));
+    const size_t nb = P->n_buckets;
+    std::lock_guard<std::mutex> lk(g_mu);          // side streams, kernel attributes
+    const std::vector<cudaStream_t> &ss = g_side_streams[P->dev];
+    if (nb > 1) CK(cudaEventRecord(P->fork, stream));
+    for (size_t bi = 0; bi < nb; bi++) {
+        const Launch &ln = P->launches[bi];
+        cudaStream_t s = (nb > 1) ? ss[bi] : stream;
+        if (nb > 1) CK(cudaStreamWaitEvent(s, P->fork, 0));
+        K.n_items = ln.n_items; K.WLp = ln.WLp; K.need_xax = ln.need_xax ? 1 : 0;
+        K.n_lo = 2; K.n_hi = a.Nt;
+        K.queue = nullptr; K.done = nullptr; K.ids = nullptr; K.ctas = nullptr;
+        if (P->verbose) {
+            cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+            t0.push_back(e0); t1.push_back(e1);
+            CK(cudaEventRecord(e0, s));
+        }
+        if (!ln.grouped) {
+            K.ids = P->d_ids + ln.off;
+            if (ln.queue) {
+                K.queue = P->d_queue + ln.q_idx; K.done = P->d_queue + P->n_buckets + ln.done_off;
+                K.q_slice = ln.q_slice; K.q_nslices = ln.q_nslices; K.q_full = ln.q_full;
+            }
+            g_configs[ln.cfg].kern<<<(unsigned)ln.grid, ln.threads, ln.smem, s>>>(K);
+        } else {
+            K.ctas = P->d_ctas + ln.off;
+            cudaLaunchConfig_t lc; memset(&lc, 0, sizeof lc);
+            lc.gridDim = dim3((unsigned)ln.grid); lc.blockDim = dim3((unsigned)ln.threads); lc.dynamicSmemBytes = ln.smem; lc.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)ln.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&lc, g_group_kernels[ln.cfg], K));
+        }
+        g_launches++;
+        CK(cudaGetLastError());
+        if (P->verbose) CK(cudaEventRecord(t1.back(), s));
+        if (nb > 1) { CK(cudaEventRecord(P->joins[bi], s)); CK(cudaStreamWaitEvent(stream, P->joins[bi], 0)); }
+    }
+    }
+    if (P->verbose) {
+        CK(cudaStreamSynchronize(stream));
+        for (size_t bi = 0; bi < t0.size(); bi++) {
+            float ms = 0, ms0 = 0;
+            cudaEventElapsedTime(&ms, t0[bi], t1[bi]); cudaEventElapsedTime(&ms0, t0[0], t1[bi]);
+            const Launch &ln = P->launches[bi];
+            fprintf(stderr, "[sfdtd] timing bucket %zu (%s cfg=%d WLp=%d cluster=%d items=%d grid=%d x %d): %.1f ms (ends at %.1f ms)\n", bi,
+                    ln.grouped ? "grouped" : "indep", ln.cfg, ln.WLp, ln.cluster, ln.n_items, ln.grid, ln.threads, ms, ms0);
+        }
+    }
+done:
+    for (cudaEvent_t e : t0) cudaEventDestroy(e);
+    for (cudaEvent_t e : t1) cudaEventDestroy(e);
+    return rc;
+}
+
+extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
+    g_err[0] = 0;
+    { const int v = validate(args); if (v != SFDTD_OK) return v; }
+    if (args->Nt <= 2) return SFDTD_OK;
+    sfdtd_plan *P = nullptr;
+    int rc = sfdtd_plan_create(args, cuda_stream, &P);
+    if (rc != SFDTD_OK) return rc;
+    rc = sfdtd_forward_plan(P, args, cuda_stream);
+    char keep[sizeof g_err]; memcpy(keep, g_err, sizeof keep);
+    sfdtd_plan_destroy(P, cuda_stream);               // stream-ordered: the scratch is released after the kernels
+    memcpy(g_err, keep, sizeof keep);
+    return rc;
+}
+
+extern "C" int sfdtd_synth_controls(const sfdtd_args *args, const sfdtd_array *f0, const sfdtd_array *x_b, const sfdtd_array *v_b,
+                                    const sfdtd_array *F_b, const sfdtd_array *u_H, void *cuda_stream) {
+    g_err[0] = 0;
+    if (!args || !args->synth) { snprintf(g_err, sizeof g_err, "args->synth is NULL"); return SFDTD_ERR_ARG; }
+    if (args->B <= 0 || args->Nt <= 0) { snprintf(g_err, sizeof g_err, "bad sizes"); return SFDTD_ERR_ARG; }
+    int rc = SFDTD_OK;
+    DeviceGuard guard;
+    KArgs K;
+    fill_kargs(K, *args);
+    const sfdtd_array none = {nullptr, 0, 0};
+    CK(guard.enter(args->synth->f0_a));
+    sfdtd_synth_controls_kernel<<<dim3((args->Nt + 127) / 128, args->B), 128, 0, (cudaStream_t)cuda_stream>>>(
+        K, f0 ? *f0 : none, x_b ? *x_b : none, v_b ? *v_b : none, F_b ? *F_b : none, u_H ? *u_H : none);
+    g_launches++;
+    CK(cudaGetLastError());
+done:
+    return rc;
+}
+
+extern "C" int sfdtd_postprocess(const sfdtd_array *uout, const sfdtd_array *zout, int32_t B, int32_t n0, int32_t n_samples,
+                                 double silence_db, int32_t normalize, int32_t bits, int64_t pcm_pitch, uint8_t *is_nan,
+                                 uint8_t *is_silent, double *gain, void *pcm_u, void *pcm_z, void *pcm_w, void *cuda_stream) {
+    g_err[0] = 0;
+    if (!uout || !zout || !uout->ptr || !zout->ptr || B <= 0 || n_samples <= 0 || n0 < 0 || (bits != 16 && bits != 24)) {
+        snprintf(g_err, sizeof g_err, "bad arguments"); return SFDTD_ERR_ARG;
+    }
+    int rc = SFDTD_OK;
+    DeviceGuard guard;
+    CK(guard.enter(uout->ptr));
+    if (bits == 16)
+        sfdtd_postprocess_kernel<16><<<B, 256, 0, (cudaStream_t)cuda_stream>>>(*uout, *zout, n0, n_samples, silence_db, normalize, is_nan,
+                                                                              is_silent, gain, (uint8_t *)pcm_u, (uint8_t *)pcm_z, (uint8_t *)pcm_w, pcm_pitch);
+    else
+        sfdtd_postprocess_kernel<24><<<B, 256, 0, (cudaStream_t)cuda_stream>>>(*uout, *zout, n0, n_samples, silence_db, normalize, is_nan,
+                                                                              is_silent, gain, (uint8_t *)pcm_u, (uint8_t *)pcm_z, (uint8_t *)pcm_w, pcm_pitch);
+    g_launches++;
+    CK(cudaGetLastError());
+done:
     return rc;
 }
