@@ -10,8 +10,13 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+LONG = ("pluck_b1_1s", "pluck_b24_1s", "allfixed_bow_b1_4s", "finehammer192_b1", "pluck_b24_01s")   # full-length fixtures
+
+
+def golden_names(long=False):
+    """short fixtures (all outputs + states), or the full-length ones of the BASELINE configs (audio only)"""
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if (n in LONG) == long]
 
 
 def load_golden(name):
@@ -34,9 +39,20 @@ def build_inputs(g, dtype=torch.float64, device="cpu"):
         state_z[:, torch.from_numpy(g["state_z_idx"]).to(device), :] = T(g["state_z_rows"])
     u0 = torch.zeros(B, 1, Nx_t1, dtype=dtype, device=device)   # never read by the stepper
     v_H = torch.zeros(B, Nt, dtype=dtype, device=device)        # never read by the stepper
-    string_params = [T(g["kappa"]), T(g["alpha"]), u0, u0.clone(), T(g["p_a"]), T(g["f0"]), T(g["pos"]), T(g["T60"])]
-    bow_params = [T(g["x_b"]), T(g["v_b"]), T(g["F_b"]), T(g["phi_0"]), T(g["phi_1"]), T(g["wid"])]
-    hammer_params = [T(g["x_H"]), v_H, T(g["u_H"]), T(g["w_H"]), T(g["M_r"]), T(g["alpha_H"])]
+
+    def C(a):   # (B,Nt) control curve; the long format stores time-constant curves as (B,1)
+        t = T(a)
+        return t.expand(B, Nt).contiguous() if (t.dim() == 2 and t.size(1) == 1 and Nt > 1) else t
+
+    if "u_H" in g:
+        u_H = T(g["u_H"])
+    else:                                                       # long format: non-zero columns only
+        u_H = torch.zeros(B, Nt, dtype=dtype, device=device)
+        if g["u_H_idx"].size:
+            u_H[:, torch.from_numpy(g["u_H_idx"]).to(device)] = T(g["u_H_cols"])
+    string_params = [T(g["kappa"]), T(g["alpha"]), u0, u0.clone(), T(g["p_a"]), C(g["f0"]), T(g["pos"]), T(g["T60"])]
+    bow_params = [C(g["x_b"]), C(g["v_b"]), C(g["F_b"]), T(g["phi_0"]), T(g["phi_1"]), C(g["wid"])]
+    hammer_params = [T(g["x_H"]), v_H, u_H, T(g["w_H"]), T(g["M_r"]), T(g["alpha_H"])]
     return dict(
         state_u=state_u, state_z=state_z, string_params=string_params, bow_params=bow_params,
         hammer_params=hammer_params,

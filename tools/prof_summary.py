@@ -40,8 +40,11 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, capture_output=True)
 cubin = [x for x in os.listdir(tmp) if x.endswith(".cubin")][0]
 li = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
-kn = re.search(r"<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:bool\))?(\d), \(?(?:int\))?(\d+), \(?(?:int\))?(\d)>", d["Kernel Name"]).groups()
-mangled = f"ILi{kn[0]}ELi{kn[1]}ELb{kn[2]}ELi{kn[3]}ELi{kn[4]}EEE"
+if "group_kernel" in d["Kernel Name"]:
+    mangled = "sfdtd_group_kernelILi" + re.search(r"group_kernel<\(?(?:int\))?(\d)>", d["Kernel Name"]).group(1) + "E"
+else:
+    kn = re.search(r"<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d)>", d["Kernel Name"]).groups()
+    mangled = f"sfdtd_step_kernelILi{kn[0]}ELi{kn[1]}ELi{kn[2]}ELi{kn[3]}EEE"
 start = [i for i, l in enumerate(li) if l.startswith(".text.") and mangled in l][0]
 end = next(i for i in range(start + 1, len(li)) if li[i].startswith("//-----"))
 cur, lines = None, []

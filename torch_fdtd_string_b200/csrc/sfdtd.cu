@@ -104,6 +104,7 @@ enum { C_WPOW = 0, C_MR, C_AHM1, C_PHI0, C_PHI1, C_RP };
 // grouped mode: what one CTA of a group's cluster runs.  A group (reference batch) is spread over the CTAs of one
 // thread-block cluster; `cls` selects the lane/row shape of all string slots of this CTA.
 constexpr int CTA_SLOTS = 8;
+constexpr int GB_MAX = 64;          // strings per group in grouped mode (a cluster holds <= 8 CTAs x 8 slots)
 struct CtaDesc {
     int32_t group;                  // group id (row of Wtab)
     int32_t cls;                    // 0: 16 lanes x 4 rows per string, 1: 32 lanes x 4 rows
@@ -297,50 +298,67 @@ template <int L> __device__ __forceinline__ int red_or(int v) {
 // any-over-CTA vote.  The barrier reduction returns the same value to every thread, but the compiler does not treat it as
 // warp-uniform: a loop that exits on it would count as divergent and every shuffle inside would be compiled with a
 // reconvergence sequence.  Passing it through a warp vote makes the uniformity visible.
-// ---- group board (grouped mode): what the strings of one group publish to each other ------------------------------
-// A group (reference batch) runs as one thread-block cluster of 128-thread CTAs.  The board is replicated at the start
-// of every CTA's shared memory and written through distributed shared memory:
-//   vote words   [2][8]          any-over-group votes, one word per CTA of the cluster, two phases
-//   step scalars [GB_MAX][6]     inputs of the hammer contact loop (hammer.cpp:28-53), published once per time step
-//   eps_u        [2][GB_MAX]     string displacement at the contact point of the current iterate, two phases
-// With the contact-loop inputs on every CTA's board, every WARP runs the scalar contact loops of all strings of the group
-// itself (one string per lane, warp votes) -- the any-over-batch vote of hammer.cpp:51 costs no barrier at all, and a time
-// step needs 1 + (outer iterations) cluster barriers instead of one per contact-loop and outer iteration.
-constexpr int GB_MAX = 64;                          // strings per group (<= 8 CTAs x 8 slots)
-constexpr int GB_HQ = GB_MAX / 32;                  // strings per lane in the warp-redundant contact loop
-constexpr int GB_VOTE = 0, GB_STEP = 8, GB_EPS = GB_STEP + 6 * GB_MAX, GB_DOUBLES = GB_EPS + 2 * GB_MAX;
-enum { GS_ETA1 = 0, GS_ETA2, GS_WR, GS_BASE, GS_HM, GS_TOLT };
+// ---- hammer contact loop of one string (hammer.cpp:28-53) ---------------------------------------------------------
+struct HamIn { double eta1, eta2, wr, base, hm, tol, k2, mhd; };   // wr = w_H^(1+alpha) relu(eta1)^(alpha-1); base = 2 u_H1 - u_H2
+// one pass: eta -> contact force, hammer displacement, next eta
+__device__ __forceinline__ double ham_pass(const HamIn &h, double eta, double eps_u, double &fo, double &uo) {
+    const double fH = (h.wr * (eta + h.eta2)) / 2;
+    fo = (h.eta1 > 0) ? fH : 0.0;
+    double tt = (h.base - h.k2 * fo) - h.mhd;
+    tt = tt > 0 ? tt : (tt != tt ? tt : 0.0);
+    uo = tt + h.mhd;
+    return (uo - eps_u) * h.hm;
+}
+// exit tests |eta - eta_estimate| > tol (hammer.cpp:49-51) of the next HAM_HB passes from `eta`, as a bit mask
+constexpr int HAM_HB = 6;
+__device__ __forceinline__ unsigned ham_mask(const HamIn &h, double eta, double eps_u) {
+    unsigned m = 0; double f_, u_;
+#pragma unroll
+    for (int p = 0; p < HAM_HB; p++) {
+        const double en = ham_pass(h, eta, eps_u, f_, u_);
+        m |= (fabs(eta - en) > h.tol ? 1u : 0u) << p;
+        eta = en;
+    }
+    return m;
+}
+
+// ---- group votes (grouped mode) --------------------------------------------------------------------------------------
+// A group (reference batch) runs as one thread-block cluster of 128-thread CTAs.  Its any-over-batch decisions
+// (string.cpp:252-253, hammer.cpp:51) are bitwise-OR votes of one 32-bit word per warp: every warp leader writes its word
+// into the vote array of every CTA of the cluster through distributed shared memory, one cluster barrier makes them
+// visible, every warp ORs the (<= 32) words itself.  The array sits at the start of every CTA's shared memory and is
+// double-buffered by phase (a warp can only be one vote ahead of the slowest warp of its group).
+constexpr int GB_DOUBLES = 32;                      // 2 phases x 32 words
 
 struct GroupComm {
-    double *board;          // this CTA's board
-    int cs, rank;           // cluster size, rank of this CTA
-    int phase;              // vote phase (CTA-uniform)
+    unsigned *vw;           // this CTA's vote array
+    int cs, rank, phase;    // cluster size, rank of this CTA, vote phase (CTA-uniform)
     __device__ __forceinline__ void init(double *smem_base) {
-        board = smem_base; phase = 0;
+        vw = (unsigned *)smem_base; phase = 0;
         cg::cluster_group cl = cg::this_cluster();
         cs = (int)cl.num_blocks(); rank = (int)cl.block_rank();
     }
     __device__ __forceinline__ void sync() const {
         if (cs > 1) cg::this_cluster().sync(); else __syncthreads();
     }
-    // one double into slot `off` of every CTA's board (visible after the next sync())
-    __device__ __forceinline__ void publish(int off, double v) const {
+    // bitwise OR of `word` over all threads of the group
+    __device__ __forceinline__ unsigned vote(unsigned word) {
+        const unsigned w = __reduce_or_sync(FULLMASK, word);
+        unsigned *slot = vw + 32 * phase;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        int nw;
         if (cs > 1) {
-            cg::cluster_group cl = cg::this_cluster();
-            for (int r = 0; r < cs; r++) cl.map_shared_rank(board, r)[off] = v;
-        } else board[off] = v;
-    }
-    // any-over-group vote; also makes everything published before it visible
-    __device__ __forceinline__ int vote(int pred) {
-        const int v = __syncthreads_or(pred);
-        if (cs == 1) return __any_sync(FULLMASK, v);
-        int *vw = (int *)(board + GB_VOTE) + 8 * phase;
-        if ((int)threadIdx.x < cs) cg::this_cluster().map_shared_rank(vw, threadIdx.x)[rank] = v;
-        cg::this_cluster().sync();
-        int r = 0;
-        for (int q = 0; q < cs; q++) r |= vw[q];
+            if (lane < cs) cg::this_cluster().map_shared_rank(slot, lane)[rank * 4 + warp] = w;
+            cg::this_cluster().sync();
+            nw = cs * 4;
+        } else {
+            if (lane == 0) slot[warp] = w;
+            __syncthreads();
+            nw = blockDim.x >> 5;
+        }
+        const unsigned r = __reduce_or_sync(FULLMASK, lane < nw ? slot[lane] : 0u);
         phase ^= 1;
-        return __any_sync(FULLMASK, r);
+        return r;
     }
 };
 template <int L> constexpr int ilog2() { return L <= 1 ? 0 : 1 + ilog2<L / 2>(); }
@@ -502,8 +520,125 @@ __host__ __device__ inline int slot_long_doubles(int W, bool grouped, int L) {
 }
 __host__ __device__ inline int long_rows(int maxNl) { return (maxNl + 1 + WL_MARGIN + 2 + 1) & ~1; }   // + 2 guards, even
 
+// loss parameters of the last step (string.cpp:119-120) -> sig0, sig1; once per string and call, not inlined
+__device__ __noinline__ void final_sigmas(const KArgs &A, int b, int Nt) {
+    const sfdtd_args &a = A.a;
+    const Derived d = derive(ctl_f0(A, b, Nt - 1), lds(a.kappa, b), lds(a.alpha, b), A);
+    const double *T60 = (const double *)a.T60.ptr + (int64_t)b * a.T60.bs;
+    const double T00 = T60[0], T01 = T60[1], T10 = T60[2], T11 = T60[3];
+    const double g2 = d.gamma * d.gamma, g4 = g2 * g2;
+    double z1, z2;
+    if (d.K > 0) {
+        const double w1 = (2 * M_PI) * T00, w2 = (2 * M_PI) * T10;
+        z1 = -g2 + sqrt(g4 + (4 * (d.K * d.K)) * (w1 * w1));
+        z2 = -g2 + sqrt(g4 + (4 * (d.K * d.K)) * (w2 * w2));
+    } else { z1 = (T00 * T00) / g2; z2 = (T10 * T10) / g2; }
+    const bool m = (T00 * T01 * T10 * T11) != 0;
+    const double s0 = m ? (-z2 / T01 + z1 / T11) : 0.0, s1 = m ? (1 / T01 - 1 / T11) : 0.0;
+    const double c6 = 13.815510557964274;
+    ((double *)a.sig0)[b] = (c6 * s0) / (z1 - z2); ((double *)a.sig1)[b] = (c6 * s1) / (z1 - z2);
+}
+
+// ---- per-step scalars of one string (grid sizes, loss, operator coefficients, bow window, readout weight) ------------
+// One call per string and time step, TB steps at a time, one step per lane.  NOT inlined: the divisions, square roots,
+// powers and (with sfdtd_synth) the control-curve evaluation are ~15 % of a stepper kernel's code but run once per step
+// and lane; one shared copy keeps the kernels' instruction footprint down (three CTAs of different phase share an SM).
+struct TabIn {
+    int b, NXT, LE, WLa;
+    bool bowm, hamm;
+    const int32_t *Wrow;
+};
+template <bool GROUPED>
+__device__ __forceinline__ void fill_table_row_impl(const KArgs &A, const TabIn &in, int n, double *t, int *ti) {
+    const sfdtd_args &a = A.a;
+    const int b = in.b;
+    const double kappa_rel = lds(a.kappa, b), alpha = lds(a.alpha, b);
+    const double *T60 = (const double *)a.T60.ptr + (int64_t)b * a.T60.bs;
+    const double T00 = T60[0], T01 = T60[1], T10 = T60[2], T11 = T60[3];
+    const double alpha2 = alpha * alpha;
+    const double xH = lds(a.x_H, b);
+    const double exc = 1.0 + (in.hamm ? 1.0 : 0.0) + (in.bowm ? 1.0 : 0.0);
+    const double f0 = ctl_f0(A, b, n);
+    const Derived d = derive(f0, kappa_rel, alpha, A);
+    const int N_t = clampN(d.Nt), N_l = clampN(d.Nl);
+    const int32_t w = in.Wrow[n];
+    const int Wt = w & 0xffff, Wl = (w >> 16) & 0xffff;
+    // loss parameters (string.cpp:100-120)
+    const double g2 = d.gamma * d.gamma, g4 = g2 * g2;
+    double z1, z2;
+    if (d.K > 0) {
+        const double w1 = (2 * M_PI) * T00, w2 = (2 * M_PI) * T10;
+        z1 = -g2 + sqrt(g4 + (4 * (d.K * d.K)) * (w1 * w1));
+        z2 = -g2 + sqrt(g4 + (4 * (d.K * d.K)) * (w2 * w2));
+    } else { z1 = (T00 * T00) / g2; z2 = (T10 * T10) / g2; }
+    const bool m = (T00 * T01 * T10 * T11) != 0;
+    const double s0 = m ? (-z2 / T01 + z1 / T11) : 0.0, s1 = m ? (1 / T01 - 1 / T11) : 0.0;
+    const double c6 = 13.815510557964274;   // 6*log(10)
+    const double sig0 = (c6 * s0) / (z1 - z2), sig1 = (c6 * s1) / (z1 - z2);
+    const double g = g2 * A.k2;
+    const double s0k = (2 * sig0) * A.k, s1k = (2 * sig1) * A.k;
+    const double phi = (g * (alpha2 - 1)) / 4;
+    const double Kk = (d.K * d.K) * A.k2;
+    const double iht = d.Nt, ihl = d.Nl;          // 1/h_t = N_t exactly
+    const double iht2 = iht * iht, iht4 = iht2 * iht2, ihl2 = ihl * ihl;
+    // operator coefficients (string.cpp:138-181; misc.cpp:119-166)
+    const double diagA = A.th + s0k + 2 * s1k * iht2, offA = 0.5 * A.omth - s1k * iht2;
+    const double kh4 = Kk * iht4;
+    const double dA = (1 + s0k) + 2 * s1k * ihl2, eA = -s1k * ihl2, idA = 1.0 / dA;
+    // bow window on the Nx_t1-point axis (bow.cpp:32, misc.cpp:20-34)
+    const double Nd = (double)in.NXT;
+    const double xb = ctl_xb(A, b, n), wd = ctl_wid(A, b, n);
+    const double ctr = __ddiv_rn(__dmul_rn(xb, (double)(N_t - 1)), Nd);
+    const double wid = __ddiv_rn(__dmul_rn(__dmul_rn(wd, d.ht), (double)(N_t - 1)), Nd);
+    const int ic = (int)fmin(fmax(floor((ctr - wid * 0.5) * Nd) - 2, 0.0), 60000.0);
+    // rows that are solved: R (see header); forced rows of a bowed string extend it
+    int R = N_t + 3;
+    if (in.bowm) { const int Rb = (int)fmin(fmax(ceil((ctr + wid * 0.5) * Nd) + 1, 0.0), 60000.0); R = max(R, Rb); }
+    if (A.a.flags & SFDTD_MANUFACTURED) R = Wt;          // every padded row is forced (string.cpp:227-232)
+    R = min(R, Wt);
+    int oob = 0;
+    if (R > in.LE) { R = in.LE; oob = 1; }
+    // homogeneous tail R..W_t-1 of A11 folded into the pivot of row R-1
+    double corr = 0.0;
+    {
+        const int mt = Wt - R;
+        if (mt > 0 && !oob) {
+            const double o2 = offA * offA;
+            double pv = diagA;
+            for (int j = 1; j < mt; j++) { const double pn = diagA - o2 * frcp(pv); if (pn == pv) break; pv = pn; }
+            corr = o2 * frcp(pv);
+        }
+    }
+    int WLs = min(N_l + 1 + WL_MARGIN, Wl);
+    if (WLs > in.WLa) { WLs = in.WLa; oob = 1; }
+    const int keep_flat = N_t + N_l + 2;                         // string.cpp:233
+    t[T_IHT] = iht; t[T_IHL] = ihl;
+    t[T_OFFA] = offA; t[T_DIAGA] = diagA; t[T_CORR] = corr;
+    t[T_OFFC] = 0.5 * A.omth + s1k * iht2; t[T_DIAGC] = A.th - s0k - 2 * s1k * iht2;
+    t[T_DIAGB] = -2 * A.th + 2 * g * iht2 + 6 * kh4; t[T_OFF1B] = -A.omth - g * iht2 - 4 * kh4; t[T_KH4] = kh4;
+    t[T_PH2] = phi * iht2; t[T_PHL] = (phi != 0.0) ? ihl * d.ht : 0.0;
+    t[T_IDA] = idA; t[T_EIDA] = eA * idA;
+    t[T_RDW] = ((0.5 * d.ht) * exc) * A.ik;                      // surface-integral weight / k (string.cpp:274-291)
+    if (GROUPED) { t[T_TOLT] = pow(d.ht, A.order); t[T_TOLL] = pow(d.hl, A.order); t[T_FB] = ctl_Fb(A, b, n); }
+    t[T_CTR] = ctr; t[T_WID] = wid;
+    t[T_VB] = ctl_vb(A, b, n);
+    t[T_UHPRE] = ctl_uH(A, b, n);
+    t[T_S0K] = s0k; t[T_S1K] = s1k; t[T_GA2] = g * alpha2;
+    ti[I_NT] = N_t; ti[I_NL] = N_l; ti[I_R] = R | (oob << 30); ti[I_WLS] = WLs;
+    ti[I_RK] = min(R, keep_flat); ti[I_KEEPL] = keep_flat - in.NXT;
+    ti[I_IDXH] = (int)fmin(fmax(floor(__dmul_rn(xH, (double)(N_t - 1))), 0.0), (double)(in.LE - 1));
+    ti[I_IC] = ic;
+}
+template <bool GROUPED>
+__device__ __noinline__ void fill_table_row(const KArgs &A, const TabIn &in, int n, double *t, int *ti) {
+    fill_table_row_impl<GROUPED>(A, in, n, t, ti);
+}
+#ifndef SFDTD_TAB_INLINE_I
+#define SFDTD_TAB_INLINE_I 1        // 1: the independent-mode kernels inline the table code (measured: the call costs them 4 %)
+#endif
+
 // ======================================================================================================
-template <int L, int ET, bool GROUPED>
+template <int L, int ET, bool GROUPED, bool MANUF>
 __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
     constexpr int TB = GROUPED ? TBS_G : TBS_I;
     constexpr int LE = L * ET;
@@ -521,12 +656,12 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
     const int sl = tid / L, ln = tid % L;
     const int nslots = blockDim.x / L;
     int b; bool valid;
-    int gi = 0, G = 1, wrow = 0;                 // grouped mode: index in the group, group size; row of the width table
+    int wrow = 0;                                // grouped mode: row of the width table
     GroupComm gc;
     if (GROUPED) {
         valid = sl < cd->n;
         const int s_ = valid ? sl : cd->n - 1;   // spare slots shadow the last string and never write, publish or vote
-        b = cd->str[s_]; gi = cd->gidx[s_]; G = cd->G; wrow = cd->group;
+        b = cd->str[s_]; wrow = cd->group;
     } else {
         const int item = blockIdx.x * nslots + sl;
         valid = item < A.n_items;
@@ -537,8 +672,9 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
     const bool surf = a.flags & SFDTD_SURFACE_INTEGRAL;
     const bool save_state = a.flags & SFDTD_SAVE_STATE;
     const bool skip_aux = a.flags & SFDTD_SKIP_AUX;
-    // the manufactured-solution mode (B = 1 verification runs) is compiled into the grouped kernels only
-    const bool manuf = GROUPED && (a.flags & SFDTD_MANUFACTURED);
+    // the manufactured-solution mode (B = 1 verification runs) has its own kernel: its per-row cosines would triple the code
+    // of every other one
+    constexpr bool manuf = MANUF;
     uint32_t status = 0;
 
     // ---- shared memory carve-up: [bow axis][fixed slot parts][longitudinal parts] ----
@@ -580,6 +716,13 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
     if (A.need_xax) {
         for (int i = tid; i < NXT; i += blockDim.x) xaxs[i] = a.xax[i];
         __syncthreads();
+    }
+    if (GROUPED) {
+        // A warp without a string leaves (barriers only wait for threads that have not exited); its vote words must read
+        // as 0, so every CTA clears its vote array before anybody in the cluster may write into it.
+        for (int i = tid; i < 64; i += blockDim.x) gc.vw[i] = 0u;
+        gc.sync();
+        if (!__any_sync(FULLMASK, valid)) return;
     }
 
     // Work queue (independent mode): the grid is sized to what is resident at once and every warp pulls one set of 32/L strings
@@ -630,8 +773,8 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
     const bool forced = bowm || hamm;
     bool group_has_hammer = false, group_has_bow = false;
     if (GROUPED) {
-        group_has_hammer = gc.vote(valid && hamm);
-        group_has_bow = gc.vote(valid && bowm);
+        const unsigned gv = gc.vote((valid && hamm ? 1u : 0u) | (valid && bowm ? 2u : 0u));
+        group_has_hammer = gv & 1u; group_has_bow = gv & 2u;
     }
     // CTA-uniform compute switches (they guard shuffles and barriers); per-string output switches
     const bool do_bow = group_has_bow || !skip_aux, do_ham = group_has_hammer || !skip_aux;
@@ -682,93 +825,20 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
     int curNt = -1, curNl = -1, ext1 = WLa, ext2 = WLa;               // ext: rows of Z1 / Z2 that may be non-zero
     float rho_h = 0.5f;                                               // contraction-rate history of the block iteration
     int s_prev = 0;                                                   // sweeps the first solve of the previous step took (warp-uniform)
+    bool have_next = false; unsigned hgm_next = 0;                    // grouped mode: contact-loop exit bits voted ahead for the next step
     __syncwarp();
 
     for (int n0 = n_lo; n0 < n_hi; n0 += TB) {
         // ================= scalar table for steps n0 .. n0+TB-1 (one step per lane) =================
         {
-            const double kappa_rel = lds(a.kappa, b), alpha = lds(a.alpha, b);
-            const double *T60 = (const double *)a.T60.ptr + (int64_t)b * a.T60.bs;
-            const double T00 = T60[0], T01 = T60[1], T10 = T60[2], T11 = T60[3];
-            const double alpha2 = alpha * alpha;
-            const double xH = lds(a.x_H, b);
-            const double exc = 1.0 + (hamm ? 1.0 : 0.0) + (bowm ? 1.0 : 0.0);
-            const int32_t *Wrow = A.Wtab + (int64_t)(GROUPED ? wrow : b / a.group_size) * Nt;
+            TabIn ti_;
+            ti_.b = b; ti_.NXT = NXT; ti_.LE = LE; ti_.WLa = WLa; ti_.bowm = bowm; ti_.hamm = hamm;
+            ti_.Wrow = A.Wtab + (int64_t)(GROUPED ? wrow : b / a.group_size) * Nt;
             for (int s = ln; s < TB; s += L) {
                 const int n = n0 + s;
                 if (n >= n_hi) break;
-                double *t = tab + s * NV;
-                int *ti = tabi + s * NI;
-                const double f0 = ctl_f0(A, b, n);
-                const Derived d = derive(f0, kappa_rel, alpha, A);
-                const int N_t = clampN(d.Nt), N_l = clampN(d.Nl);
-                const int32_t w = Wrow[n];
-                const int Wt = w & 0xffff, Wl = (w >> 16) & 0xffff;
-                // loss parameters (string.cpp:100-120)
-                const double g2 = d.gamma * d.gamma, g4 = g2 * g2;
-                double z1, z2;
-                if (d.K > 0) {
-                    const double w1 = (2 * M_PI) * T00, w2 = (2 * M_PI) * T10;
-                    z1 = -g2 + sqrt(g4 + (4 * (d.K * d.K)) * (w1 * w1));
-                    z2 = -g2 + sqrt(g4 + (4 * (d.K * d.K)) * (w2 * w2));
-                } else { z1 = (T00 * T00) / g2; z2 = (T10 * T10) / g2; }
-                const bool m = (T00 * T01 * T10 * T11) != 0;
-                const double s0 = m ? (-z2 / T01 + z1 / T11) : 0.0, s1 = m ? (1 / T01 - 1 / T11) : 0.0;
-                const double c6 = 13.815510557964274;   // 6*log(10)
-                const double sig0 = (c6 * s0) / (z1 - z2), sig1 = (c6 * s1) / (z1 - z2);
-                const double g = g2 * A.k2;
-                const double s0k = (2 * sig0) * A.k, s1k = (2 * sig1) * A.k;
-                const double phi = (g * (alpha2 - 1)) / 4;
-                const double Kk = (d.K * d.K) * A.k2;
-                const double iht = d.Nt, ihl = d.Nl;          // 1/h_t = N_t exactly
-                const double iht2 = iht * iht, iht4 = iht2 * iht2, ihl2 = ihl * ihl;
-                // operator coefficients (string.cpp:138-181; misc.cpp:119-166)
-                const double diagA = A.th + s0k + 2 * s1k * iht2, offA = 0.5 * A.omth - s1k * iht2;
-                const double kh4 = Kk * iht4;
-                const double dA = (1 + s0k) + 2 * s1k * ihl2, eA = -s1k * ihl2, idA = 1.0 / dA;
-                // bow window on the Nx_t1-point axis (bow.cpp:32, misc.cpp:20-34)
-                const double Nd = (double)NXT;
-                const double xb = ctl_xb(A, b, n), wd = ctl_wid(A, b, n);
-                const double ctr = __ddiv_rn(__dmul_rn(xb, (double)(N_t - 1)), Nd);
-                const double wid = __ddiv_rn(__dmul_rn(__dmul_rn(wd, d.ht), (double)(N_t - 1)), Nd);
-                const int ic = (int)fmin(fmax(floor((ctr - wid * 0.5) * Nd) - 2, 0.0), 60000.0);
-                // rows that are solved: R (see header); forced rows of a bowed string extend it
-                int R = N_t + 3;
-                if (bowm) { const int Rb = (int)fmin(fmax(ceil((ctr + wid * 0.5) * Nd) + 1, 0.0), 60000.0); R = max(R, Rb); }
-                if (a.flags & SFDTD_MANUFACTURED) R = Wt;          // every padded row is forced (string.cpp:227-232)
-                R = min(R, Wt);
-                int oob = 0;
-                if (R > LE) { R = LE; oob = 1; }
-                // homogeneous tail R..W_t-1 of A11 folded into the pivot of row R-1
-                double corr = 0.0;
-                {
-                    const int mt = Wt - R;
-                    if (mt > 0 && !oob) {
-                        const double o2 = offA * offA;
-                        double pv = diagA;
-                        for (int j = 1; j < mt; j++) { const double pn = diagA - o2 * frcp(pv); if (pn == pv) break; pv = pn; }
-                        corr = o2 * frcp(pv);
-                    }
-                }
-                int WLs = min(N_l + 1 + WL_MARGIN, Wl);
-                if (WLs > WLa) { WLs = WLa; oob = 1; }
-                const int keep_flat = N_t + N_l + 2;                         // string.cpp:233
-                t[T_IHT] = iht; t[T_IHL] = ihl;
-                t[T_OFFA] = offA; t[T_DIAGA] = diagA; t[T_CORR] = corr;
-                t[T_OFFC] = 0.5 * A.omth + s1k * iht2; t[T_DIAGC] = A.th - s0k - 2 * s1k * iht2;
-                t[T_DIAGB] = -2 * A.th + 2 * g * iht2 + 6 * kh4; t[T_OFF1B] = -A.omth - g * iht2 - 4 * kh4; t[T_KH4] = kh4;
-                t[T_PH2] = phi * iht2; t[T_PHL] = (phi != 0.0) ? ihl * d.ht : 0.0;
-                t[T_IDA] = idA; t[T_EIDA] = eA * idA;
-                t[T_RDW] = ((0.5 * d.ht) * exc) * A.ik;                      // surface-integral weight / k (string.cpp:274-291)
-                if (GROUPED) { t[T_TOLT] = pow(d.ht, A.order); t[T_TOLL] = pow(d.hl, A.order); t[T_FB] = ctl_Fb(A, b, n); }
-                t[T_CTR] = ctr; t[T_WID] = wid;
-                t[T_VB] = ctl_vb(A, b, n);
-                t[T_UHPRE] = ctl_uH(A, b, n);
-                t[T_S0K] = s0k; t[T_S1K] = s1k; t[T_GA2] = g * alpha2;
-                ti[I_NT] = N_t; ti[I_NL] = N_l; ti[I_R] = R | (oob << 30); ti[I_WLS] = WLs;
-                ti[I_RK] = min(R, keep_flat); ti[I_KEEPL] = keep_flat - NXT;
-                ti[I_IDXH] = (int)fmin(fmax(floor(__dmul_rn(xH, (double)(N_t - 1))), 0.0), (double)(LE - 1));
-                ti[I_IC] = ic;
+                if (!GROUPED && SFDTD_TAB_INLINE_I) fill_table_row_impl<GROUPED>(A, ti_, n, tab + s * NV, tabi + s * NI);
+                else fill_table_row<GROUPED>(A, ti_, n, tab + s * NV, tabi + s * NI);
             }
         }
         __syncwarp();
@@ -1170,18 +1240,20 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                 for (int r = 0; r < ET; r++) nu[r] = S[u1o + PRL(r)];
                 for (int j = ln; j < WLa; j += L) Lb[zpo + j] = Lb[z1o + j];
                 __syncwarp();
-                // contact-loop inputs of this string onto the board of every CTA of the group (once per step)
-                const double hbase = (2 * uH1) - uH2;
+                // hammer contact loop (hammer.cpp:28-53).  Every string iterates its own scalar loop; only the exit test is an
+                // any-over-batch vote.  The exit tests of the next HAM_HB passes are evaluated ahead of time and travel as a bit
+                // mask in one vote word: the group leaves the loop after the first pass whose bit is clear for every string.
+                HamIn hin;
+                hin.eta1 = eta1; hin.eta2 = eta2; hin.wr = cst[C_WPOW] * r1pow; hin.base = (2 * uH1) - uH2; hin.hm = hm; hin.tol = tol_t;
+                hin.k2 = k2; hin.mhd = A.mhd;
+                double eps_u = 0.0;
+                unsigned hgm = 0;                  // exit-test bits of the coming contact loop, OR-ed over the group
                 if (GROUPED && group_has_hammer) {
-                    const double eps0 = fetch_row<L, ET>(nu, idxH);
-                    if (ln == 0 && valid) {
-                        const int o = GB_STEP + 6 * gi;
-                        gc.publish(o + GS_ETA1, eta1); gc.publish(o + GS_ETA2, eta2);
-                        gc.publish(o + GS_WR, cst[C_WPOW] * r1pow); gc.publish(o + GS_BASE, hbase);
-                        gc.publish(o + GS_HM, hm); gc.publish(o + GS_TOLT, tol_t);
-                        gc.publish(GB_EPS + gi, eps0);
-                    }
-                    gc.sync();
+                    eps_u = fetch_row<L, ET>(nu, idxH);
+                    // (normally the mask already came with the last vote of the previous step, see below)
+                    if (have_next) hgm = hgm_next;
+                    else hgm = gc.vote((valid ? ham_mask(hin, eta1 * hm, eps_u) : 0u) << 1) >> 1;
+                    have_next = false;
                 }
                 int iter = 0;
                 bool solved = false;
@@ -1210,50 +1282,26 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     }
                     // hammer loop (hammer.cpp:28-53); its exit test is an any-over-batch vote
                     if (do_ham && GROUPED && group_has_hammer) {
-                        // every warp iterates the scalar loops of ALL strings of the group (lane q: strings q, q + 32)
-                        const double *bd = gc.board + GB_STEP, *be = gc.board + GB_EPS + (iter & 1) * GB_MAX;
-                        const int lane = tid & 31;
-                        // (the loop inputs are re-read from the board every pass: registers are scarce here, the loop runs 1-3 passes)
-                        double est[GB_HQ], fq[GB_HQ], uq[GB_HQ];
-                        int qi[GB_HQ];
-#pragma unroll
-                        for (int h = 0; h < GB_HQ; h++) {
-                            qi[h] = min(lane + 32 * h, G - 1);
-                            est[h] = bd[6 * qi[h] + GS_ETA1] * bd[6 * qi[h] + GS_HM]; fq[h] = 0.0; uq[h] = 0.0;
+                        constexpr unsigned FULL = (1u << HAM_HB) - 1u;
+                        double eta = eta1 * hm;
+                        int hit = 0;
+                        for (;;) {
+                            const bool full = (hgm & FULL) == FULL;            // no pass of this chunk ends the loop
+                            int np = full ? HAM_HB : __ffs((int)(~hgm & FULL));
+                            bool cap = false;
+                            if (hit + np >= A.max_iter) { np = A.max_iter - hit; cap = true; }
+                            for (int p = 0; p < np; p++) eta = ham_pass(hin, eta, eps_u, FH, uH);
+                            hit += np;
+                            if (cap) { if (full) status |= SFDTD_ST_HAMMER_CAP; break; }
+                            if (!full) break;
+                            hgm = gc.vote((valid ? ham_mask(hin, eta, eps_u) : 0u) << 1) >> 1;
                         }
-                        int hit = 0, more;
-                        do {
-                            int nc = 0;
-#pragma unroll
-                            for (int h = 0; h < GB_HQ; h++) {
-                                const double *bq = bd + 6 * qi[h];
-                                const double eta = est[h];
-                                const double fH = (bq[GS_WR] * (eta + bq[GS_ETA2])) / 2;
-                                fq[h] = (bq[GS_ETA1] > 0) ? fH : 0.0;
-                                double tt = (bq[GS_BASE] - k2 * fq[h]) - A.mhd;
-                                tt = tt > 0 ? tt : (tt != tt ? tt : 0.0);
-                                uq[h] = tt + A.mhd;
-                                est[h] = (uq[h] - be[qi[h]]) * bq[GS_HM];
-                                nc |= (lane + 32 * h < G) && (fabs(eta - est[h]) > bq[GS_TOLT]);
-                            }
-                            hit++;
-                            more = __any_sync(FULLMASK, nc);
-                            if (hit >= A.max_iter) { if (more) status |= SFDTD_ST_HAMMER_CAP; more = 0; }
-                        } while (more);
                         cnt_ham += hit;
-                        // this string's force and hammer displacement sit in lane gi % 32
-                        double f0v = __shfl_sync(FULLMASK, fq[0], gi & 31), u0v = __shfl_sync(FULLMASK, uq[0], gi & 31);
-#pragma unroll
-                        for (int h = 1; h < GB_HQ; h++) {
-                            const double f1v = __shfl_sync(FULLMASK, fq[h], gi & 31), u1v = __shfl_sync(FULLMASK, uq[h], gi & 31);
-                            if ((gi >> 5) == h) { f0v = f1v; u0v = u1v; }
-                        }
-                        FH = f0v; uH = u0v;
                     } else if (do_ham) {
                         // no hammered string in the group: eta = 0 for every string, the loop ends after one pass
-                        const double fH = ((cst[C_WPOW] * r1pow) * (0.0 + eta2)) / 2;
+                        const double fH = (hin.wr * (0.0 + eta2)) / 2;
                         FH = (eta1 > 0) ? fH : 0.0;
-                        double tt = (hbase - k2 * FH) - A.mhd;
+                        double tt = (hin.base - k2 * FH) - A.mhd;
                         tt = tt > 0 ? tt : (tt != tt ? tt : 0.0);
                         uH = tt + A.mhd;
                         cnt_ham += 1;
@@ -1304,14 +1352,37 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     // a string whose linear iteration diverges has no fixed point to wait for: it does not vote
                     const int not_conv = !capped && ((nc_t && !nan_u) || (nc_l && !nan_z));
                     iter++;
+                    unsigned word = (valid && not_conv) ? 1u : 0u;
+                    bool spec = false;
                     if (GROUPED && group_has_hammer) {
-                        // contact-point displacement of the new iterate for the next pass (made visible by the vote's barrier)
-                        const double epsn = fetch_row<L, ET>(nu, idxH);
-                        if (ln == 0 && valid) gc.publish(GB_EPS + (iter & 1) * GB_MAX + gi, epsn);
+                        // exit tests of the next pass's contact loop (contact-point displacement of the new iterate) ride along ...
+                        eps_u = fetch_row<L, ET>(nu, idxH);
+                        if (valid) word |= ham_mask(hin, eta1 * hm, eps_u) << 1;
+                        // ... and so do those of the NEXT STEP's first contact loop, in case this pass turns out to be the last
+                        // one of the step: everything they need (new state row, hammer displacement of this pass, the next
+                        // step's table row) is known here.  Saves the step's own vote (one cluster barrier of three).
+                        spec = !save_state && !manuf && (jj + 1 < jmax);
+                        if (spec) {
+                            const double *tn = tab + (jj + 1) * NV;
+                            const int *tin = tabi + (jj + 1) * NI;
+                            const int idxHn = tin[I_IDXH];
+                            const double mkn = (idxHn <= tin[I_NT]) ? 1.0 : 0.0;
+                            const double uH1n = t[T_UHPRE] + (out_ham ? uH : 0.0);
+                            const double u1n = fetch_row<L, ET>(nu, idxHn), u2n = S[u1o + PR(idxHn)];
+                            HamIn hn;
+                            hn.eta1 = uH1n - u1n * mkn; hn.eta2 = uH1 - u2n * mkn;
+                            const double r1n = hn.eta1 > 0 ? hn.eta1 : (hn.eta1 != hn.eta1 ? hn.eta1 : 0.0);
+                            const double ex = cst[C_AHM1];
+                            hn.wr = cst[C_WPOW] * ((ex == 2.0) ? r1n * r1n : ((ex == 0.0) ? 1.0 : pow(r1n, ex)));
+                            hn.base = (2 * uH1n) - uH1; hn.hm = hm; hn.tol = tn[T_TOLT]; hn.k2 = k2; hn.mhd = A.mhd;
+                            if (valid) word |= ham_mask(hn, hn.eta1 * hm, u1n) << (1 + HAM_HB);
+                        }
                     }
-                    int more = gc.vote(valid && not_conv);
+                    const unsigned gvw = gc.vote(word);
+                    hgm = gvw >> 1;
+                    int more = gvw & 1u;
                     if (iter >= A.max_iter) { if (more) status |= SFDTD_ST_OUTER_CAP; more = 0; }
-                    if (!more) break;
+                    if (!more) { have_next = spec; hgm_next = gvw >> (1 + HAM_HB); break; }
                 }
                 cnt_outer += iter;
             }
@@ -1427,23 +1498,7 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
         }
         if (ln == 0 && !a.u_H.ptr && A.uH_carry) { A.uH_carry[2 * (int64_t)b] = uH2; A.uH_carry[2 * (int64_t)b + 1] = uH1; }
         if (ln == 0) {
-            if (Nt > 2 && qst[1] == Nt) {
-                // loss parameters of the last step (string.cpp:119-120)
-                const Derived d = derive(ctl_f0(A, b, Nt - 1), lds(a.kappa, b), lds(a.alpha, b), A);
-                const double *T60 = (const double *)a.T60.ptr + (int64_t)b * a.T60.bs;
-                const double T00 = T60[0], T01 = T60[1], T10 = T60[2], T11 = T60[3];
-                const double g2 = d.gamma * d.gamma, g4 = g2 * g2;
-                double z1, z2;
-                if (d.K > 0) {
-                    const double w1 = (2 * M_PI) * T00, w2 = (2 * M_PI) * T10;
-                    z1 = -g2 + sqrt(g4 + (4 * (d.K * d.K)) * (w1 * w1));
-                    z2 = -g2 + sqrt(g4 + (4 * (d.K * d.K)) * (w2 * w2));
-                } else { z1 = (T00 * T00) / g2; z2 = (T10 * T10) / g2; }
-                const bool m = (T00 * T01 * T10 * T11) != 0;
-                const double s0 = m ? (-z2 / T01 + z1 / T11) : 0.0, s1 = m ? (1 / T01 - 1 / T11) : 0.0;
-                const double c6 = 13.815510557964274;
-                ((double *)a.sig0)[b] = (c6 * s0) / (z1 - z2); ((double *)a.sig1)[b] = (c6 * s1) / (z1 - z2);
-            }
+            if (Nt > 2 && qst[1] == Nt) final_sigmas(A, b, Nt);
             // time slices of one call accumulate (the caller zero-initialises both arrays)
             if (a.status) a.status[b] |= status_all;
             if (a.counters) {
@@ -1467,19 +1522,25 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
 // independent mode: strings of unforced groups, any warp of any CTA
 template <int L, int ET, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_constant__ KArgs A) {
-    step_body<L, ET, false>(A, nullptr);
+    step_body<L, ET, false, false>(A, nullptr);
 }
 // grouped mode: one thread-block cluster of 128-thread CTAs per group; the CTA's descriptor picks the lane/row shape of its
 // string slots.  KIND 0: strings of <= 64 rows on 16 lanes x 4 rows, <= 128 rows on 32 lanes x 4 rows (168 registers, three
-// CTAs per SM -- of different groups, so that one group's barrier waits are filled by the others);  KIND 1: 32 lanes x 8 rows.
+// CTAs per SM -- of different groups, so that one group's barrier waits are filled by the others);  KIND 1: 32 lanes x 8 rows;
+// KIND 2: 32 lanes x 8 rows with the manufactured-solution forcing (vnv.cpp).
+#ifndef SFDTD_GROUP_MINB
+#define SFDTD_GROUP_MINB 3
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(128, KIND == 0 ? 3 : 1) sfdtd_group_kernel(const __grid_constant__ KArgs A) {
+__global__ void __launch_bounds__(128, KIND == 0 ? SFDTD_GROUP_MINB : 1) sfdtd_group_kernel(const __grid_constant__ KArgs A) {
     const CtaDesc *cd = A.ctas + blockIdx.x;
     if (KIND == 0) {
-        if (cd->cls == 0) step_body<16, 4, true>(A, cd);
-        else step_body<32, 4, true>(A, cd);
+        if (cd->cls == 0) step_body<16, 4, true, false>(A, cd);
+        else step_body<32, 4, true, false>(A, cd);
+    } else if (KIND == 1) {
+        step_body<32, 8, true, false>(A, cd);
     } else {
-        step_body<32, 8, true>(A, cd);
+        step_body<32, 8, true, true>(A, cd);
     }
 }
 
@@ -1599,9 +1660,9 @@ const Config g_configs[] = {   // smallest first
 #endif
 constexpr int N_CONFIGS = sizeof(g_configs) / sizeof(g_configs[0]);
 // grouped-mode kernels and the slot shapes of their CTA classes
-void (*const g_group_kernels[2])(const KArgs) = {sfdtd_group_kernel<0>, sfdtd_group_kernel<1>};
+void (*const g_group_kernels[3])(const KArgs) = {sfdtd_group_kernel<0>, sfdtd_group_kernel<1>, sfdtd_group_kernel<2>};
 struct GShape { int L, ET; };
-const GShape g_gshape[2][2] = {{{16, 4}, {32, 4}}, {{32, 8}, {32, 8}}};
+const GShape g_gshape[3][2] = {{{16, 4}, {32, 4}}, {{32, 8}, {32, 8}}, {{32, 8}, {32, 8}}};
 
 // longitudinal allocation classes of the independent mode (rows incl. the two guards)
 int wl_class(int rows, int c_min = 16) {
@@ -1857,7 +1918,7 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
             snprintf(g_err, sizeof g_err, "group %d: %d strings with bowed / hammered ones (grouped mode holds <= %d per group)", g, G, GB_MAX);
             rc = SFDTD_ERR_UNSUPPORTED; goto done;
         }
-        int kind = 0;
+        int kind = manuf ? 2 : 0;
         std::vector<int> cls(G);
         for (int s = 0; s < G; s++) {
             const int rows = rows_of(g0 + s);
@@ -1865,17 +1926,17 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
                 snprintf(g_err, sizeof g_err, "string %d: %d transverse rows are outside the built kernel set", g0 + s, rows);
                 rc = SFDTD_ERR_UNSUPPORTED; goto done;
             }
-            if (rows > 128) kind = 1;
+            if (rows > 128 && kind == 0) kind = 1;
             cls[s] = (rows > 64 || lanes_of(g0 + s) > 16) ? 1 : 0;
         }
         std::vector<CtaDesc> ctas;
         for (int c = 0; c < 2; c++) {
-            const int per = (kind == 1) ? 4 : (c == 0 ? 8 : 4);
+            const int per = (kind != 0) ? 4 : (c == 0 ? 8 : 4);
             CtaDesc cd; memset(&cd, 0, sizeof cd);
-            cd.group = g; cd.cls = (kind == 1) ? 0 : c; cd.G = G;
+            cd.group = g; cd.cls = (kind != 0) ? 0 : c; cd.G = G;
             for (int s = 0; s < G; s++) {
                 if (kind == 0 && cls[s] != c) continue;
-                if (kind == 1 && c == 1) continue;
+                if (kind != 0 && c == 1) continue;
                 cd.str[cd.n] = g0 + s; cd.gidx[cd.n] = s; cd.n++;
                 if (cd.n == per) { ctas.push_back(cd); cd.n = 0; }
             }
