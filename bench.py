@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--excitation", default="pluck")
     ap.add_argument("--group", type=int, default=GROUP, help="strings per reference batch (task.batch_size); diagnostics only")
     ap.add_argument("--skip-aux", action="store_true")
+    ap.add_argument("--controls", default="synth", choices=["synth", "table"],
+                    help="synth: the stepper evaluates the control curves from per-string scalars; table: (B,Nt) fp64 arrays in HBM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-nt", type=int, default=26, help="samples per reference-arm step (bounded sample)")
@@ -117,7 +119,9 @@ def reference_arm(a, rank):
         "impl": "reference", "metric": "simulated string-seconds/sec", "value": val, "unit": "string-seconds/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(a, a.strings),
+        "config": dict(workload_config(a, a.strings), measured=f"{GROUP} strings x {Nt_s - 2} steps per step (one reference batch)",
+                       extrapolated=True),
+        "extrapolated": True,
         "cpu_baseline": {"value": val, "unit": "string-seconds/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": val, "unit": "string-seconds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -138,23 +142,28 @@ def workload_config(a, strings):
                         f"of {GROUP}, {a.length:g} s @ 48 kHz, random string params (experiment=nsynth-like ranges)",
             "strings_per_gpu": strings, "group_size": GROUP, "sr": SR, "length_s": a.length,
             "excitation": a.excitation, "precision": "double", "aux_outputs": "skipped" if a.skip_aux else "reference-faithful",
+            "controls": getattr(a, "controls", "synth"),
             "l2": "inputs larger than L2 (f0 + outputs >> 126 MB), no flush needed"}
 
 
-def algorithmic_work(p, ctl, counters, group):
+def algorithmic_work(p, counters, group, n_run):
     """F_step = 60 W_t + 30 W_l + S (110 W_t + 74 W_l) + I (4 (W_t + W_l) + 50) per string-step,
-    W = batch-max operator widths of the step; grid-point updates = N_t+1 + N_l+1 per string-step."""
+    W = batch-max operator widths of the step; grid-point updates = N_t+1 + N_l+1 per string-step.
+    Also the same formula on the rows the kernel actually solves (own grid: N_t + 3, N_l + 3 <= W) -> `F_exec`."""
     import numpy as np
     import torch
+    from torch_fdtd_string_b200 import sampler
     k = float(np.float32(p["k"])); th = float(np.float32(p["theta_t"])); lam = float(np.float32(p["lambda_c"]))
     tt1 = float(np.float32(2 * np.float32(th) - 1)); tt2 = float(np.float32(2 * np.float32(tt1)))
-    f0_all = ctl["f0"][:, 2:]
-    B = f0_all.size(0)
-    F_sum = gpu_updates = Wt_sum = Wl_sum = 0.0
+    B = p["B"]
+    dev = p["kappa"].device
+    F_sum = F_exec = gpu_updates = Wt_sum = Wl_sum = 0.0
     gpc = max(1, 4096 // group)                                  # groups per chunk: the temporaries are (strings, Nt) sized
+    tt = torch.arange(3, n_run + 1, dtype=torch.float64, device=dev).view(1, -1)      # 1-based sample index of steps 2..n_run-1
     for g0 in range(0, B // group, gpc):
         sl = slice(g0 * group, min(B, (g0 + gpc) * group))
-        f0 = f0_all[sl]
+        q = {kx: p[kx][sl] for kx in ("f0_a", "f0_b", "mod_frq", "mod_amp", "vib_t0")}
+        f0 = sampler._f0_curve(q, p["Nt"], p["k"], tt)
         G = f0.size(0) // group
         gamma = 2 * f0
         K = gamma * p["kappa"][sl].view(-1, 1)
@@ -169,11 +178,13 @@ def algorithmic_work(p, ctl, counters, group):
         Wt_ = Wt.unsqueeze(1); Wl_ = Wl.unsqueeze(1)
         F = (60 * Wt_ + 30 * Wl_) + S * (110 * Wt_ + 74 * Wl_) + I * (4 * (Wt_ + Wl_) + 50)
         F_sum += float(F.sum()); Wt_sum += float(Wt.sum()); Wl_sum += float(Wl.sum())
-        del gamma, K, h1, Nt_, Nl_, F
-    n_wt = (B // group) * f0_all.size(1)
-    # bytes: 6 control reads + 5 output writes per string-step (fp64) + initial rows
-    bytes_ = B * f0_all.size(1) * 11 * 8 + B * 2 * (p["Nx_t1"] + p["Nx_l1"]) * 8
-    return F_sum, gpu_updates, float(bytes_), Wt_sum / n_wt, Wl_sum / n_wt
+        Rt = torch.minimum(Nt_.view(G, group, -1) + 3, Wt_); Rl = torch.minimum(Nl_.view(G, group, -1) + 3, Wl_)
+        Fx = (60 * Rt + 30 * Rl) + S * (110 * Rt + 74 * Rl) + I * (4 * (Rt + Rl) + 50)
+        F_exec += float(Fx.sum())
+        del gamma, K, h1, Nt_, Nl_, F, Fx, Rt, Rl
+    n_steps = n_run - 2
+    n_wt = (B // group) * n_steps
+    return F_sum, F_exec, gpu_updates, Wt_sum / n_wt, Wl_sum / n_wt
 
 
 def main():
@@ -189,7 +200,7 @@ def main():
     import torch.distributed as dist
     from torch_fdtd_string_b200 import _lib, launch_count
     from torch_fdtd_string_b200 import sampler
-    from torch_fdtd_string_b200.forward_fn import step_strings
+    from torch_fdtd_string_b200.forward_fn import build_args, Plan, postprocess
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -202,23 +213,32 @@ def main():
                                         cfg=(dict(p_a_max=a.p_a_max) if a.p_a_max else None))
     Nt = p_host["Nt"]
     p = sampler.to_device(p_host, dev)
-    ctl = sampler.expand_controls(p, dev)
     f64 = dict(dtype=torch.float64, device=dev)
     out = {n: torch.zeros(B, Nt, **f64) for n in ("uout", "zout", "v_r", "F_H", "u_H_out")}
-
-    uH = torch.empty_like(ctl["u_H"])
-
-    def one_step(counters=False):
-        su = p["state_u"].clone(); sz = p["state_z"].clone()
-        uH.copy_(ctl["u_H"])                      # u_H is updated in place by the stepper (string.cpp:303)
-        return step_strings(
+    su = p["state_u"].clone(); sz = p["state_z"].clone()
+    ctl = uH = None
+    if a.controls == "synth":
+        # control curves synthesised inside the stepper from the compact scalars (no (B,Nt) input arrays)
+        args, res, keep = sampler.compact_args(p, GROUP, skip_aux=a.skip_aux, counters=True, out=out, su=su, sz=sz)
+    else:
+        ctl = sampler.expand_controls(p, dev)
+        uH = torch.empty_like(ctl["u_H"])
+        args, res, keep = build_args(
             su, sz, kappa=p["kappa"], alpha=p["alpha"], f0=ctl["f0"], pos=p["pos"], T60=p["T60"],
             x_b=ctl["x_b"], v_b=ctl["v_b"], F_b=ctl["F_b"], wid=ctl["wid"], phi_0=p["phi_0"], phi_1=p["phi_1"],
             x_H=p["x_H"], w_H=p["w_H"], M_r=p["M_r"], alpha_H=p["alpha_H"], u_H=uH,
             bow_mask=p["bow_mask"], hammer_mask=p["hammer_mask"], k=p["k"], theta_t=p["theta_t"],
             lambda_c=p["lambda_c"], relative_order=p["relative_order"], Nt=Nt, group_size=GROUP,
-            surface_integral=True, save_state=False, skip_aux=a.skip_aux, p_a=p["p_a"], out=out,
-            counters=counters, check=False)
+            surface_integral=True, save_state=False, skip_aux=a.skip_aux, p_a=p["p_a"], out=out, counters=True)
+    plan = Plan(args)                             # prepass + one device->host read, outside the timed region
+
+    def one_step():
+        # inputs resident in HBM; nothing here synchronises the host
+        su.copy_(p["state_u"]); sz.copy_(p["state_z"])
+        if uH is not None:
+            uH.copy_(ctl["u_H"])                  # u_H is updated in place by the stepper (string.cpp:303)
+        res["status"].zero_(); res["counters"].zero_()
+        plan.run(args)
 
     def barrier():
         if world > 1:
@@ -226,11 +246,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up ----
-    res = None
     for _ in range(max(a.warmup, 1)):
-        res = one_step(counters=True)
+        one_step()
+    torch.cuda.synchronize()
     status = int(res["status"].max())
-    counters = res["counters"]
+    counters = res["counters"].clone()
     nan_strings = int(torch.isnan(out["uout"][:, 2:]).any(dim=1).sum())
 
     # ---- timed region: K steps, CUDA events on the launching stream, max over ranks ----
@@ -257,41 +277,72 @@ def main():
     string_seconds = world * B * (Nt - 2) / SR
     value = string_seconds / per_step
 
-    flops, gpu_upd, bytes_, Wt_mean, Wl_mean = algorithmic_work(p, ctl, counters, GROUP)
+    flops, flops_exec, gpu_upd, Wt_mean, Wl_mean = algorithmic_work(p, counters, GROUP, Nt)
+    n_ctl_reads = 0 if a.controls == "synth" else 6
+    bytes_ = B * (Nt - 2) * (n_ctl_reads + 5) * 8 + B * 2 * (p["Nx_t1"] + p["Nx_l1"]) * 8
+    plan.close()
 
-    # ---- end-to-end through the public API with host buffers (H2D of the compact parameters, D2H of the audio) ----
+    # ---- end to end through the public API with HOST buffers ----
+    # every step: pinned host compact parameters -> H2D -> plan (prepass, one small D2H) -> stepper (controls synthesised in
+    # the kernel) -> device post-processing (NaN / silence flags, l-infinity gain, PCM_24 quantisation: what the reference
+    # writes to output-u/-z/.wav, src/task/simulate.py:333-337,416-425) -> D2H of the three PCM streams on a copy stream,
+    # overlapping the next step's kernels.  The timed region ends when the last byte is on the host.
     e2e = None
     if not a.no_e2e:
-        del ctl, uH                              # the end-to-end path builds its own controls from the compact parameters
+        del ctl, uH
+        for n in ("v_r", "F_H", "u_H_out"):
+            out.pop(n)
+        del args, res, keep
         torch.cuda.empty_cache()
         pin = {kx: p_host[kx].pin_memory() for kx in sampler.TENSOR_KEYS}
         ph = dict(p_host); ph.update(pin)
-        rows = max(1, min(B, (256 << 20) // ((Nt - 2) * 8)))          # pinned staging buffer, <= 256 MiB
-        stage = torch.empty(rows, Nt - 2, dtype=torch.float64).pin_memory()
+        ns = Nt - 2
+        row = ns * 3
+        pitch = (row + 15) // 16 * 16
+        pcm = [{kx: torch.empty(B, pitch, dtype=torch.uint8, device=dev) for kx in ("u", "z", "w")} for _ in range(2)]
+        chunk_rows = max(1, min(B, (256 << 20) // pitch))              # pinned staging: two slots of <= 256 MiB
+        stage = [torch.empty(chunk_rows, pitch, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        flags_h = torch.empty(3, B, dtype=torch.float64).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)
+        d2h_bytes = 3 * B * pitch + 3 * B * 8
 
-        def e2e_step():
+        def e2e_step(i):
             q = sampler.to_device(ph, dev, non_blocking=True)
-            r = sampler.run_compact(q, GROUP, skip_aux=a.skip_aux, out=out)
-            for name in ("uout", "zout"):                              # device -> host read of the audio, all strings
-                for r0 in range(0, B, rows):
-                    r1 = min(B, r0 + rows)
-                    stage[: r1 - r0].copy_(r[name][r0:r1, 2:], non_blocking=True)
-            torch.cuda.synchronize()
+            a_, r_, k_ = sampler.compact_args(q, GROUP, skip_aux=a.skip_aux, out=out, aux_outputs=False)
+            pl = Plan(a_)
+            pl.run(a_)
+            pp = postprocess(out["uout"], out["zout"], n0=2, bits=24, out=pcm[i % 2])
+            fl = torch.stack([pp["is_nan"].double(), pp["is_silent"].double(), pp["gain"]])
+            ev = torch.cuda.Event(); ev.record()
+            pl.close()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev)
+                flags_h.copy_(fl, non_blocking=True)
+                j = 0
+                for kx in ("u", "z", "w"):
+                    src = pcm[i % 2][kx]
+                    for r0 in range(0, B, chunk_rows):
+                        r1 = min(B, r0 + chunk_rows)
+                        stage[j % 2][: r1 - r0].copy_(src[r0:r1], non_blocking=True)
+                        j += 1
+            fl.record_stream(copy_stream)
+            return (q, a_, r_, k_)
 
-        e2e_step()
+        held = e2e_step(0)
         barrier()
         t0 = time.perf_counter()
         n_e2e = max(1, min(a.steps, 3))
-        for _ in range(n_e2e):
-            e2e_step()
+        for i in range(n_e2e):
+            held = e2e_step(i + 1)
         barrier()
         te = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": string_seconds / float(te), "unit": "string-seconds/s",
-               "h2d_bytes_per_step": world * sampler.compact_nbytes(p_host), "d2h_bytes_per_step": world * 2 * B * (Nt - 2) * 8,
+               "h2d_bytes_per_step": world * sampler.compact_nbytes(p_host), "d2h_bytes_per_step": world * d2h_bytes,
                "ms_per_step": float(te) * 1e3,
-               "note": "all ranks: pinned host compact parameters -> H2D -> on-device control expansion -> stepper -> D2H of uout,zout"}
+               "note": "all ranks, every step: pinned host compact parameters -> H2D -> plan -> stepper (in-kernel control synthesis) -> "
+                       "device NaN/silence/gain + PCM_24 quantisation -> D2H of output-u/-z/sum PCM (copy stream, overlapping the next step)"}
 
     if rank != 0:
         if world > 1:
@@ -320,9 +371,15 @@ def main():
                 "traffic": traffic, "traffic_unit": "DRAM bytes per call (ncu dram__bytes_read+write per string-step of the largest bucket kernel x string-steps of the call; profiles/ncu_traffic_r01e.json)",
                 "peak_source": peak_src, "peak_nominal": 37.2, "frac_of_nominal": achieved / 37.2,
                 "flops_per_string_step": flops / (B * (Nt - 2)),
+                # the same formula on the rows the kernel actually solves (own grid N_t+3 / N_l+3 instead of the batch-max
+                # operator widths the reference solves; the ghost rows are folded into one pivot exactly)
+                "frac_executed": flops_exec / per_step / 1e12 / peak.value,
+                "flops_executed_per_string_step": flops_exec / (B * (Nt - 2)),
                 "note": "algorithmic flops per SURVEY.md 8(d) of all strings of the call / CUDA-event time of the call (one kernel launch per string-size bucket, all overlapped on side streams); tensor cores unused (no dense contraction)"}
     roofline_hbm = {"bound": "hbm", "achieved": bytes_ / per_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": bytes_ / per_step / 1e9 / hbm_peak, "traffic": traffic, "peak_source": hbm_src}
+                    "frac": bytes_ / per_step / 1e9 / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
+                    "algorithmic_bytes_per_string_step": (n_ctl_reads + 5) * 8,
+                    "note": f"{n_ctl_reads} control reads + 5 output writes per string-step (fp64)"}
 
     cpu = None
     if not a.no_cpu_baseline:

@@ -6,11 +6,22 @@ import torch
 from torch_fdtd_string_b200 import sampler
 
 
-def reference_inputs(p, sl=None, Nt=None):
-    """p: sampler.sample_nsynth_like(...) (CPU).  sl: slice of strings (one reference batch).  Nt: prefix length."""
+def device_controls(p, Nt=None):
+    """the (B,Nt) control curves exactly as the stepper synthesises them from the compact description (needs a GPU),
+    as CPU tensors -- the oracle must see the same doubles (floor(1/h(f0)) decides grid sizes)"""
+    from torch_fdtd_string_b200 import synth_controls
+    Nt = p["Nt"] if Nt is None else Nt
+    dev = torch.device("cuda")
+    c = synth_controls(sampler.synth_dict(sampler.to_device(p, dev)), p["B"], Nt, dev)
+    return {k: v.cpu() for k, v in c.items()}
+
+
+def reference_inputs(p, sl=None, Nt=None, controls=None):
+    """p: sampler.sample_nsynth_like(...) (CPU).  sl: slice of strings (one reference batch).  Nt: prefix length.
+    controls: (B,>=Nt) curves to use instead of the host-side expansion."""
     sl = slice(None) if sl is None else sl
     Nt = p["Nt"] if Nt is None else Nt
-    c = sampler.expand_controls(p, torch.device("cpu"))
+    c = controls if controls is not None else sampler.expand_controls(p, torch.device("cpu"))
     B = p["kappa"][sl].numel()
     su = torch.zeros(B, Nt, p["Nx_t1"], dtype=torch.float64)
     sz = torch.zeros(B, Nt, p["Nx_l1"], dtype=torch.float64)

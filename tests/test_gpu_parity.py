@@ -50,6 +50,89 @@ def test_cuda_matches_reference_golden(name):
         assert gu.rel_l2(out["state_u"].cpu().numpy(), g["state_u_full"]) < tol
 
 
+# ---- the BASELINE configs at their stated length (fixtures: audio only, made by tests/golden/make_golden.py) ----------
+# measured relative L2 of the CUDA path against the unmodified reference (B200, this round) -> gate = 100 x measured,
+# never looser than the 1e-6 of north_star
+FULL_LENGTH = {
+    # name: keys compared
+    "pluck_b1_1s": ("uout", "zout", "v_r_out", "F_H_out", "u_H_out"),          # configs[0]: 47 998 samples
+    "finehammer192_b1": ("uout", "zout", "v_r_out", "F_H_out", "u_H_out"),     # configs[3] at 192 kHz: 9 598 samples, N_t = 237
+    "allfixed_bow_b1_4s": ("uout", "zout", "v_r_out"),                         # configs[2]: 191 998 samples
+}
+FULL_LENGTH_GATE = {"pluck_b1_1s": 1e-6, "finehammer192_b1": 1e-6, "allfixed_bow_b1_4s": 1e-6}
+
+
+def _have(name):
+    import os
+    return os.path.exists(os.path.join(gu.GOLDEN_DIR, f"{name}.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(FULL_LENGTH))
+def test_full_length_config_matches_reference(name):
+    if not _have(name):
+        pytest.skip(f"fixture {name} not generated")
+    g = gu.load_golden(name)
+    out, inp = run_cuda(g)
+    errs = {}
+    for k in FULL_LENGTH[name]:
+        assert tuple(out[k].shape) == g[k].shape, (k, out[k].shape, g[k].shape)      # bit-exact sample counts (Nt - 2)
+        errs[k] = gu.rel_l2(out[k].cpu().numpy(), g[k])
+    errs["state_u_last"] = gu.rel_l2(out["state_u"][:, -2:, :].cpu().numpy(), g["state_u_last"])
+    errs["state_z_last"] = gu.rel_l2(out["state_z"][:, -2:, :].cpu().numpy(), g["state_z_last"])
+    print(name, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert not np.isnan(g["uout"]).any()
+    for k, v in errs.items():
+        assert v < FULL_LENGTH_GATE[name], (name, k, v)
+
+
+def test_nsynth_batch_full_length_nan_mask_and_per_string_parity():
+    """BASELINE configs[1]: one nsynth-like reference batch (24 strings, 1 s @ 48 kHz, fp64) at full length.
+    * the set of strings that blow up to NaN is the reference's, and they do so at (nearly) the same sample
+      (reference src/task/simulate.py:91-93,333-334 drops them);
+    * every other string matches the reference per string: <= 1e-6 relative L2 over the whole second, except where the
+      REFERENCE ITSELF is more sensitive than that -- measured by running the unmodified reference on the same inputs with
+      state_u * (1 + 2^-50) (`pert_*` arrays of the fixture): there the bound is 100 x the reference's own distance."""
+    name = "pluck_b24_1s"
+    if not _have(name):
+        pytest.skip(f"fixture {name} not generated")
+    g = gu.load_golden(name)
+    out, _ = run_cuda(g)
+    rep = []
+    for key in ("uout", "zout"):
+        x = out[key].cpu().numpy(); r = g[key]
+        assert x.shape == r.shape
+        bad_x, bad_r = ~np.isfinite(x), ~np.isfinite(r)
+        nan_x, nan_r = bad_x.any(1), bad_r.any(1)
+        on_x = np.where(nan_x, bad_x.argmax(1), -1); on_r = np.where(nan_r, bad_r.argmax(1), -1)
+        win = int(g["pert_win"]) if "pert_win" in g else 480
+        for b in range(x.shape[0]):
+            if nan_r[b] or nan_x[b]:
+                # NaN strings: same set; onset within the reference's own sensitivity window (its perturbed run's onset) or 10 ms
+                assert nan_r[b] and nan_x[b], (key, b, "NaN mask differs", int(on_x[b]), int(on_r[b]))
+                slack = 480
+                if f"pert_{key}_nan_onset" in g and g[f"pert_{key}_nan_onset"][b] >= 0:
+                    slack = max(slack, 2 * abs(int(g[f"pert_{key}_nan_onset"][b]) - int(on_r[b])))
+                assert abs(int(on_x[b]) - int(on_r[b])) <= slack, (key, b, int(on_x[b]), int(on_r[b]), slack)
+                n_ok = max(0, min(int(on_x[b]), int(on_r[b])) - 4800)      # compare up to 0.1 s before the blow-up
+            else:
+                n_ok = x.shape[1]
+            if n_ok < win:
+                rep.append((key, b, "nan-early", None, None)); continue
+            err = np.linalg.norm(x[b, :n_ok] - r[b, :n_ok]) / np.linalg.norm(r[b, :n_ok])
+            tol = 1e-6
+            if f"pert_{key}_err" in g:
+                nw = n_ok // win
+                sens = np.sqrt((g[f"pert_{key}_err"][b, :nw] ** 2).sum()) / max(np.sqrt((g[f"pert_{key}_norm"][b, :nw] ** 2).sum()), 1e-300)
+                tol = max(tol, 100 * sens)
+            rep.append((key, b, "ok" if err < tol else "FAIL", float(err), float(tol)))
+    for row in rep:
+        print(row)
+    assert not [r for r in rep if r[2] == "FAIL"]
+    # most strings of the batch must meet the plain 1e-6 bound (the sensitive ones are a minority)
+    plain = [r for r in rep if r[0] == "uout" and r[3] is not None and r[3] < 1e-6]
+    assert len(plain) >= 12, len(plain)
+
+
 def test_chunked_equals_unchunked_on_gpu():
     g = gu.load_golden("hammer_b2_chunked")
     a, _ = run_cuda(g)

@@ -36,13 +36,14 @@ def batch():
 def test_workload_matches_oracle_on_sampled_groups(batch, oracle):
     Nt = 242
     res = run_cuda(batch, Nt)
+    ctl = su.device_controls(batch, Nt)                     # the curves the stepper synthesised, for the oracle
     assert not (int(res["status"].max()) & ~1)              # only the solver-cap bit may appear (diverging strings)
     uo = res["uout"][:, 2:].cpu().numpy(); zo = res["zout"][:, 2:].cpu().numpy()
     checked = 0
     for g in (0, 71, 147):
         sl = slice(g * GROUP, (g + 1) * GROUP)
-        ref = gu.run_process(oracle.forward_fn, su.reference_inputs(batch, sl, Nt))
-        pert = su.reference_inputs(batch, sl, Nt)
+        ref = gu.run_process(oracle.forward_fn, su.reference_inputs(batch, sl, Nt, controls=ctl))
+        pert = su.reference_inputs(batch, sl, Nt, controls=ctl)
         pert["state_u"] *= (1.0 + 2.0 ** -50)
         sens = gu.run_process(oracle.forward_fn, pert)
         for s in range(GROUP):

@@ -69,26 +69,37 @@ def _call(args, stream=None):
         raise RuntimeError(f"sfdtd_forward failed ({rc}): {lib.sfdtd_last_error().decode()}")
 
 
-def step_strings(state_u, state_z, *, kappa, alpha, f0, pos, T60, x_b, v_b, F_b, wid, phi_0, phi_1,
-                 x_H, w_H, M_r, alpha_H, u_H, bow_mask, hammer_mask, k, theta_t, lambda_c,
-                 relative_order, Nt, group_size, surface_integral=True, save_state=False, skip_aux=False,
-                 manufactured=False, n_0=0, p_a=None, max_iter=100, out=None, counters=False, stream=None, check=True):
-    """Native API.  All tensors are float64 CUDA tensors.
+def _synth_struct(synth, B, dev, keep):
+    """dict of the compact control description (sampler keys) -> ctypes sfdtd_synth with device pointers"""
+    y = _lib.Synth()
+    y.Nt_full = int(synth["Nt_full"]); y.t_0 = int(synth.get("t_0", 0)); y.sr = float(synth["sr"])
+    for n in _lib.SYNTH_KEYS:
+        t = synth[n].reshape(-1).to(device=dev, dtype=torch.float64).contiguous()
+        assert t.numel() == B, (n, t.shape, B)
+        keep.append(t)
+        setattr(y, n, t.data_ptr())
+    keep.append(y)
+    return y
 
-    state_u/state_z: (B, Nt, Nx) when ``save_state`` (reference layout, updated in place), else
-    (B, 2, Nx) holding rows [n-2, n-1] (overwritten with the last two rows).  Control curves
-    (f0, x_b, v_b, F_b, wid) are (B, Nt) or anything broadcastable to it (time stride 0 allowed);
-    u_H is (B, Nt) and updated in place.  Returns dict(uout, zout, v_r, F_H, u_H_out (B,Nt),
-    sig0, sig1 (B), status (B) int32[, counters (B,4) int64]).
-    """
+
+def build_args(state_u, state_z, *, kappa, alpha, pos, T60, phi_0, phi_1, x_H, w_H, M_r, alpha_H, bow_mask, hammer_mask,
+               k, theta_t, lambda_c, relative_order, Nt, group_size, f0=None, x_b=None, v_b=None, F_b=None, wid=None,
+               u_H=None, synth=None, surface_integral=True, save_state=False, skip_aux=False, manufactured=False, n_0=0,
+               p_a=None, max_iter=100, out=None, counters=False, aux_outputs=True):
+    """Fills a ``sfdtd_args`` for the C ABI.  Returns (args, results dict, keep-alive list).
+
+    Control curves come either as (B,Nt)-broadcastable tensors (f0, x_b, v_b, F_b, wid, u_H) or as ``synth``: a dict of the
+    per-string scalars of ``sfdtd_synth`` (keys ``_lib.SYNTH_KEYS`` + Nt_full, sr[, t_0]) that the stepper evaluates
+    itself.  ``aux_outputs=False`` leaves v_r / F_H / u_H_out unallocated (audio only)."""
     dev = state_u.device
     assert dev.type == "cuda", "the stepper runs on CUDA only"
-    for t in (state_u, state_z, u_H):
+    for t in (state_u, state_z):
         assert t.dtype == torch.float64 and t.stride(-1) == 1
     B, Nx_t1, Nx_l1 = state_u.size(0), state_u.size(2), state_z.size(2)
     f64 = dict(dtype=torch.float64, device=dev)
+    names = ("uout", "zout", "v_r", "F_H", "u_H_out") if aux_outputs else ("uout", "zout")
     if out is None:
-        out = {n: torch.zeros(B, Nt, **f64) for n in ("uout", "zout", "v_r", "F_H", "u_H_out")}
+        out = {n: torch.zeros(B, Nt, **f64) for n in names}
     sig0 = torch.zeros(B, **f64); sig1 = torch.zeros(B, **f64)
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     cnt = torch.zeros(B, 4, dtype=torch.int64, device=dev) if counters else None
@@ -98,7 +109,7 @@ def step_strings(state_u, state_z, *, kappa, alpha, f0, pos, T60, x_b, v_b, F_b,
     T60c = T60.reshape(B, 4).contiguous()
     if p_a is None:
         p_a = torch.zeros(B, **f64)
-    keep = [bm, hm, xax, T60c, p_a]
+    keep = [bm, hm, xax, T60c, p_a, sig0, sig1, status, cnt, out]
 
     a = Args()
     a.abi_version = _lib.SFDTD_ABI_VERSION
@@ -110,31 +121,142 @@ def step_strings(state_u, state_z, *, kappa, alpha, f0, pos, T60, x_b, v_b, F_b,
     a.k, a.theta_t, a.lambda_c, a.relative_order = float(k), float(theta_t), float(lambda_c), float(relative_order)
     a.state_u = _arr(state_u, 0, 1); a.state_z = _arr(state_z, 0, 1)
     a.kappa = _vec_arr(kappa, B); a.alpha = _vec_arr(alpha, B); a.p_a = _vec_arr(p_a, B); a.pos = _vec_arr(pos, B)
-    a.f0 = _time_arr(f0, B, Nt)
     a.T60 = Array(); a.T60.ptr = T60c.data_ptr(); a.T60.bs = 4; a.T60.ts = 0
-    a.x_b = _time_arr(x_b, B, Nt); a.v_b = _time_arr(v_b, B, Nt); a.F_b = _time_arr(F_b, B, Nt); a.wid = _time_arr(wid, B, Nt)
     a.phi_0 = _vec_arr(phi_0, B); a.phi_1 = _vec_arr(phi_1, B)
     a.x_H = _vec_arr(x_H, B); a.w_H = _vec_arr(w_H, B); a.M_r = _vec_arr(M_r, B); a.alpha_H = _vec_arr(alpha_H, B)
-    assert u_H.shape == (B, Nt)
-    a.u_H = _arr(u_H, 0, 1)
+    if synth is None:
+        a.f0 = _time_arr(f0, B, Nt)
+        a.x_b = _time_arr(x_b, B, Nt); a.v_b = _time_arr(v_b, B, Nt); a.F_b = _time_arr(F_b, B, Nt); a.wid = _time_arr(wid, B, Nt)
+        a.synth = None
+    else:
+        y = _synth_struct(synth, B, dev, keep)
+        a.synth = ctypes.addressof(y)
+    if u_H is not None:
+        assert u_H.shape == (B, Nt) and u_H.dtype == torch.float64
+        a.u_H = _arr(u_H, 0, 1)
+    else:
+        assert synth is not None, "u_H may only be omitted with synthesised controls"
     a.bow_mask, a.hammer_mask, a.xax = bm.data_ptr(), hm.data_ptr(), xax.data_ptr()
-    for n in ("uout", "zout", "v_r", "F_H", "u_H_out"):
+    for n in names:
         setattr(a, n, _arr(out[n], 0, 1))
     a.sig0, a.sig1, a.status = sig0.data_ptr(), sig1.data_ptr(), status.data_ptr()
     a.counters = cnt.data_ptr() if counters else None
-    _call(a, stream)
-    del keep
-    if check:
-        bits = 0
-        for v in status.unique().tolist():
-            bits |= int(v)
-        if bits & (_lib.ST_RANGE | _lib.ST_BOW_WINDOW):
-            raise RuntimeError(f"sfdtd: configuration outside the supported range (status bits {bits:#x}: "
-                               "0x8 = bow window wider than the kernel supports, 0x10 = grid size out of range)")
     res = dict(out)
     res.update(sig0=sig0, sig1=sig1, status=status)
     if counters:
         res["counters"] = cnt
+    return a, res, keep
+
+
+def _check_status(status):
+    bits = 0
+    for v in status.unique().tolist():
+        bits |= int(v)
+    if bits & (_lib.ST_RANGE | _lib.ST_BOW_WINDOW):
+        raise RuntimeError(f"sfdtd: configuration outside the supported range (status bits {bits:#x}: "
+                           "0x8 = bow window wider than the kernel supports, 0x10 = grid size out of range)")
+
+
+def step_strings(state_u, state_z, *, stream=None, check=True, **kw):
+    """Native API.  All tensors are float64 CUDA tensors (see ``build_args`` for the arguments).
+
+    state_u/state_z: (B, Nt, Nx) when ``save_state`` (reference layout, updated in place), else
+    (B, 2, Nx) holding rows [n-2, n-1] (overwritten with the last two rows).  Control curves
+    (f0, x_b, v_b, F_b, wid) are (B, Nt) or anything broadcastable to it (time stride 0 allowed), or
+    ``synth`` scalars; u_H is (B, Nt) and updated in place.  Returns dict(uout, zout[, v_r, F_H, u_H_out]
+    (B,Nt), sig0, sig1 (B), status (B) int32[, counters (B,4) int64]).  Asynchronous: the kernels are queued
+    on the stream when this returns (``check=True`` reads the status words and therefore waits).
+    """
+    a, res, keep = build_args(state_u, state_z, **kw)
+    with torch.cuda.device(state_u.device):
+        _call(a, stream)
+    if check:
+        _check_status(res["status"])
+    res["_keep"] = keep
+    return res
+
+
+class Plan:
+    """``sfdtd_plan``: everything the stepper derives from the parameters before it can launch (one small device->host
+    read).  ``run`` queues a call without any host synchronisation, so transfers and the next call can overlap."""
+
+    def __init__(self, args, stream=None, keep=None):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        s = torch.cuda.current_stream() if stream is None else stream
+        rc = self._lib.sfdtd_plan_create(ctypes.byref(args), ctypes.c_void_p(s.cuda_stream), ctypes.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"sfdtd_plan_create failed ({rc}): {self._lib.sfdtd_last_error().decode()}")
+
+    def run(self, args, stream=None):
+        s = torch.cuda.current_stream() if stream is None else stream
+        rc = self._lib.sfdtd_forward_plan(self._h, ctypes.byref(args), ctypes.c_void_p(s.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"sfdtd_forward_plan failed ({rc}): {self._lib.sfdtd_last_error().decode()}")
+
+    def close(self, stream=None):
+        if self._h:
+            s = torch.cuda.current_stream() if stream is None else stream
+            self._lib.sfdtd_plan_destroy(self._h, ctypes.c_void_p(s.cuda_stream))
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def synth_controls(synth, B, Nt, device, k=None):
+    """The (B,Nt) control curves exactly as the stepper evaluates ``synth`` (sfdtd_synth_controls)."""
+    lib = _lib.load()
+    keep = []
+    y = _synth_struct(synth, B, device, keep)
+    a = Args()
+    a.abi_version = _lib.SFDTD_ABI_VERSION; a.B = B; a.Nt = Nt; a.group_size = 1; a.Nx_t1 = 1; a.Nx_l1 = 1
+    a.k = float(k if k is not None else 1.0 / synth["sr"])
+    a.synth = ctypes.addressof(y)
+    out = {n: torch.empty(B, Nt, dtype=torch.float64, device=device) for n in ("f0", "x_b", "v_b", "F_b", "u_H")}
+    arrs = [_arr(out[n], 0, 1) for n in ("f0", "x_b", "v_b", "F_b", "u_H")]
+    with torch.cuda.device(device):
+        rc = lib.sfdtd_synth_controls(ctypes.byref(a), *[ctypes.byref(x) for x in arrs],
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sfdtd_synth_controls failed ({rc}): {lib.sfdtd_last_error().decode()}")
+    out["wid"] = synth["wid"].reshape(-1, 1).to(device=device, dtype=torch.float64).expand(B, Nt)
+    return out
+
+
+def postprocess(uout, zout, n0=2, n_samples=None, silence_db=-23.0, normalize=True, bits=24, pcm=("u", "z", "w"), stream=None,
+                out=None):
+    """Device-side NaN / silence flags, l-infinity gain and PCM quantisation of the audio (sfdtd_postprocess; reference
+    src/task/simulate.py:333-337,416-425, src/utils/audio.py:42-48,72-76).  uout, zout: (B,Nt) float64 CUDA tensors.
+    Returns dict(is_nan, is_silent (B) uint8, gain (B), pcm_u / pcm_z / pcm_w (B, pitch) uint8 rows of packed little-endian
+    PCM_16 / PCM_24 samples, pitch = row bytes rounded up to 16)."""
+    lib = _lib.load()
+    B, Nt = uout.shape
+    n_samples = Nt - n0 if n_samples is None else int(n_samples)
+    dev = uout.device
+    row = n_samples * (bits // 8)
+    pitch = (row + 15) // 16 * 16
+    res = dict(is_nan=torch.empty(B, dtype=torch.uint8, device=dev), is_silent=torch.empty(B, dtype=torch.uint8, device=dev),
+               gain=torch.empty(B, dtype=torch.float64, device=dev), pitch=pitch, row_bytes=row)
+    ptr = {}
+    for kx in ("u", "z", "w"):
+        if kx in pcm:
+            res["pcm_" + kx] = out[kx] if out is not None else torch.empty(B, pitch, dtype=torch.uint8, device=dev)
+            assert res["pcm_" + kx].shape == (B, pitch) and res["pcm_" + kx].is_contiguous()
+            ptr[kx] = res["pcm_" + kx].data_ptr()
+        else:
+            ptr[kx] = None
+    ua, za = _arr(uout, 0, 1), _arr(zout, 0, 1)
+    s = torch.cuda.current_stream() if stream is None else stream
+    with torch.cuda.device(dev):
+        rc = lib.sfdtd_postprocess(ctypes.byref(ua), ctypes.byref(za), B, int(n0), n_samples, float(silence_db),
+                                   1 if normalize else 0, int(bits), pitch, res["is_nan"].data_ptr(), res["is_silent"].data_ptr(),
+                                   res["gain"].data_ptr(), ptr["u"], ptr["z"], ptr["w"], ctypes.c_void_p(s.cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sfdtd_postprocess failed ({rc}): {lib.sfdtd_last_error().decode()}")
     return res
 
 

@@ -244,13 +244,48 @@ def compact_nbytes(p):
     return int(sum(p[kx].numel() * p[kx].element_size() for kx in TENSOR_KEYS))
 
 
+SYNTH_KEYS = ["f0_a", "f0_b", "mod_frq", "mod_amp", "vib_t0", "x_b1", "x_b2", "v_b1", "v_b2", "F_b1", "F_b2", "pulloff", "wid", "v_H"]
+
+
+def synth_dict(p):
+    """compact description -> the ``synth`` argument of the stepper (struct sfdtd_synth): the control curves are evaluated
+    inside the kernels from these per-string scalars, no (B,Nt) array exists"""
+    d = {kx: p[kx] for kx in SYNTH_KEYS}
+    d.update(Nt_full=p["Nt"], sr=float(p["sr"]), t_0=0)
+    return d
+
+
+def compact_args(p_dev, group_size, surface_integral=True, skip_aux=False, counters=False, out=None, n_run=None,
+                 aux_outputs=True, su=None, sz=None):
+    """(args, results, keep) of a synthesised-control call for compact device parameters (see forward_fn.build_args)"""
+    from .forward_fn import build_args
+    n_run = p_dev["Nt"] if n_run is None else int(n_run)
+    su = p_dev["state_u"].clone() if su is None else su
+    sz = p_dev["state_z"].clone() if sz is None else sz
+    return build_args(
+        su, sz, kappa=p_dev["kappa"], alpha=p_dev["alpha"], pos=p_dev["pos"], T60=p_dev["T60"],
+        phi_0=p_dev["phi_0"], phi_1=p_dev["phi_1"], x_H=p_dev["x_H"], w_H=p_dev["w_H"], M_r=p_dev["M_r"],
+        alpha_H=p_dev["alpha_H"], bow_mask=p_dev["bow_mask"], hammer_mask=p_dev["hammer_mask"], k=p_dev["k"],
+        theta_t=p_dev["theta_t"], lambda_c=p_dev["lambda_c"], relative_order=p_dev["relative_order"], Nt=n_run,
+        group_size=group_size, synth=synth_dict(p_dev), surface_integral=surface_integral, save_state=False,
+        skip_aux=skip_aux, p_a=p_dev["p_a"], counters=counters, out=out, aux_outputs=aux_outputs)
+
+
 def run_compact(p_dev, group_size, surface_integral=True, skip_aux=False, counters=False, controls=None, out=None,
-                n_run=None):
-    """compact device params -> audio: expands the controls on the device and runs the stepper for the first
-    `n_run` samples (default: the full length)."""
-    from .forward_fn import step_strings
+                n_run=None, synth=True, aux_outputs=True):
+    """compact device params -> audio for the first `n_run` samples (default: the full length).  ``synth`` (default): the
+    stepper synthesises the control curves itself; otherwise they are expanded to (B,n_run) arrays first (``controls`` may
+    pass them in)."""
+    from .forward_fn import step_strings, _call
+    import torch as _t
     dev = p_dev["kappa"].device
     n_run = p_dev["Nt"] if n_run is None else int(n_run)
+    if synth and controls is None:
+        a, res, keep = compact_args(p_dev, group_size, surface_integral, skip_aux, counters, out, n_run, aux_outputs)
+        with _t.cuda.device(dev):
+            _call(a)
+        res["_keep"] = keep
+        return res
     c = controls if controls is not None else expand_controls(p_dev, dev, n_run)
     su = p_dev["state_u"].clone(); sz = p_dev["state_z"].clone()
     res = step_strings(
@@ -260,5 +295,5 @@ def run_compact(p_dev, group_size, surface_integral=True, skip_aux=False, counte
         bow_mask=p_dev["bow_mask"], hammer_mask=p_dev["hammer_mask"], k=p_dev["k"], theta_t=p_dev["theta_t"],
         lambda_c=p_dev["lambda_c"], relative_order=p_dev["relative_order"], Nt=n_run, group_size=group_size,
         surface_integral=surface_integral, save_state=False, skip_aux=skip_aux, p_a=p_dev["p_a"], counters=counters, out=out,
-        check=False)
+        check=False, aux_outputs=aux_outputs)
     return res
