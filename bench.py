@@ -44,6 +44,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-nt", type=int, default=26, help="samples per reference-arm step (bounded sample)")
+    ap.add_argument("--sweep", default="", help="comma-separated TOTAL string counts (BASELINE configs[4]: 1024,4096,16384,65536,"
+                    "262144,1048576): each point is sharded over the ranks and run in waves of <= --strings per call, audio only")
+    ap.add_argument("--no-drop-in", action="store_true", help="skip the reference-signature forward_fn leg")
+    ap.add_argument("--async-steps", action="store_true", help="diagnostics: queue all timed steps without synchronising the host in "
+                    "between (measured 10-15 %% slower per step on B200: launches queued behind a running call slow it down)")
     ap.add_argument("--p-a-max", type=float, default=None, help="override the pluck amplitude cap (diagnostics only)")
     return ap.parse_args()
 
@@ -187,6 +192,105 @@ def algorithmic_work(p, counters, group, n_run):
     return F_sum, F_exec, gpu_updates, Wt_sum / n_wt, Wl_sum / n_wt
 
 
+def run_sweep(a, points, rank, world, dev):
+    """BASELINE configs[4]: batch sweep.  Every point = `total` nsynth-like strings in reference batches of GROUP, sharded
+    over the ranks (whole batches, no collective), run in waves of <= a.strings strings per call with in-kernel control
+    synthesis and audio-only outputs.  Kernel time = CUDA events around every wave's call (plan creation and host sampling
+    excluded), max over ranks; wall time includes them."""
+    import torch
+    import torch.distributed as dist
+    from torch_fdtd_string_b200 import sampler
+    from torch_fdtd_string_b200.forward_fn import Plan
+    rows = []
+    wave_cap = (a.strings // GROUP) * GROUP
+    for total in points:
+        groups = max(1, total // GROUP)
+        mine = len(range(rank, groups, world)) * GROUP                 # round-robin over ranks (parallel.rank_batches)
+        done, t_k, waves, nan = 0, 0.0, 0, 0
+        out = None
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        while done < mine:
+            n = min(wave_cap, mine - done)
+            ph = sampler.sample_nsynth_like(n, sr=SR, length=a.length, excitation=a.excitation, seed=50000 + 97 * rank + waves + total)
+            p = sampler.to_device(ph, dev)
+            Nt = ph["Nt"]
+            if out is None or out["uout"].size(0) != n:
+                out = {k: torch.empty(n, Nt, dtype=torch.float64, device=dev) for k in ("uout", "zout")}
+            args, res, keep = sampler.compact_args(p, GROUP, skip_aux=a.skip_aux, out=out, aux_outputs=False)
+            plan = Plan(args)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); plan.run(args); e1.record()
+            torch.cuda.synchronize()
+            t_k += e0.elapsed_time(e1) * 1e-3
+            nan += int(torch.isnan(out["uout"][:, -1]).sum())
+            plan.close()
+            done += n; waves += 1
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([t_k, wall, float(nan)], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            t_k, wall, nan = float(mx[0]), float(mx[1]), int(sm[2])
+        ss = groups * GROUP * (int(SR * a.length) - 2) / SR
+        rows.append({"strings_total": groups * GROUP, "strings_per_gpu_max": -(-groups // world) * GROUP, "waves_per_gpu": waves,
+                     "value": ss / t_k if t_k > 0 else None, "ms_kernel": t_k * 1e3, "wall_value": ss / wall, "nan_strings": nan})
+        if rank == 0:
+            print(f"[sweep] {rows[-1]}", file=sys.stderr, flush=True)
+    return rows
+
+
+def run_drop_in(a, dev, batches=4):
+    """The literal drop-in: the reference's own call -- forward_fn(state_u (B,Nt,Nx), ...) with B = 24 fat tensors, one
+    batch per call (src/task/simulate.py:65-76), `batches` calls = BASELINE configs[1] (num_samples=100 -> 4 batches) --
+    (a) one after the other like the reference's loop (src/task/simulate.py:272), (b) all in flight on their own streams
+    (torch_fdtd_string_b200.deferred_checks).  A single batch is 12 warps on a 148-SM GPU and its time loop is sequential:
+    this path is latency-bound whatever the kernel does; the native API above is what fills the GPU."""
+    import torch
+    from torch_fdtd_string_b200 import sampler, forward_fn, deferred_checks
+    Nt = int(SR * a.length)
+    calls = []
+    for i in range(batches):
+        ph = sampler.sample_nsynth_like(GROUP, sr=SR, length=a.length, excitation=a.excitation, seed=900 + i)
+        p = sampler.to_device(ph, dev)
+        c = sampler.expand_controls(p, dev)
+        su = torch.zeros(GROUP, Nt, ph["Nx_t1"], dtype=torch.float64, device=dev); su[:, :2] = p["state_u"]
+        sz = torch.zeros(GROUP, Nt, ph["Nx_l1"], dtype=torch.float64, device=dev); sz[:, :2] = p["state_z"]
+        u0 = torch.zeros(GROUP, 1, ph["Nx_t1"], dtype=torch.float64, device=dev)
+        sp = [p["kappa"], p["alpha"], u0, u0, p["p_a"].view(-1, 1, 1), c["f0"], p["pos"], p["T60"]]
+        bp = [c["x_b"], c["v_b"], c["F_b"], p["phi_0"], p["phi_1"], c["wid"].contiguous()]
+        hp = [p["x_H"], torch.zeros(GROUP, Nt, dtype=torch.float64, device=dev), c["u_H"], p["w_H"], p["M_r"], p["alpha_H"]]
+        calls.append((su, sz, sp, bp, hp, p["bow_mask"].view(-1, 1, 1), p["hammer_mask"].view(-1, 1, 1),
+                      [ph["k"], ph["theta_t"], ph["lambda_c"]], float(ph["relative_order"]), True, False, 0, Nt))
+
+    def reset():
+        for cl in calls:
+            cl[0][:, 2:].zero_(); cl[1][:, 2:].zero_(); cl[4][2][:, 2:].zero_()
+        torch.cuda.synchronize()
+
+    forward_fn(*calls[0]); reset()                                      # warm-up
+    t0 = time.perf_counter()
+    for cl in calls:
+        forward_fn(*cl)
+        torch.cuda.synchronize()
+    t_seq = time.perf_counter() - t0
+    reset()
+    streams = [torch.cuda.Stream(device=dev) for _ in calls]
+    t0 = time.perf_counter()
+    with deferred_checks():
+        for st, cl in zip(streams, calls):
+            with torch.cuda.stream(st):
+                forward_fn(*cl)
+    t_par = time.perf_counter() - t0
+    ss = batches * GROUP * (Nt - 2) / SR
+    return {"api": "forward_fn(state_u (B,Nt,Nx), ...) -- the reference's call, B = 24, SAVE_STATE", "batches": batches,
+            "sequential": {"value": ss / t_seq, "unit": "string-seconds/s", "ms_per_batch": t_seq / batches * 1e3},
+            "in_flight": {"value": ss / t_par, "unit": "string-seconds/s", "ms_total": t_par * 1e3, "streams": batches},
+            "note": "wall clock incl. launches and the final synchronise; tensors resident on the device"}
+
+
 def main():
     global GROUP
     a = parse()
@@ -263,6 +367,8 @@ def main():
     for _ in range(a.steps):
         one_step()
         ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append(ev)
+        if not a.async_steps:
+            torch.cuda.synchronize()        # the host waits for each step like a caller that consumes its result would
     e1.record()
     barrier()
     t_dev = e0.elapsed_time(e1) * 1e-3
@@ -331,7 +437,7 @@ def main():
         held = e2e_step(0)
         barrier()
         t0 = time.perf_counter()
-        n_e2e = max(1, min(a.steps, 3))
+        n_e2e = max(1, min(a.steps, 8))
         for i in range(n_e2e):
             held = e2e_step(i + 1)
         barrier()
@@ -344,6 +450,17 @@ def main():
                "note": "all ranks, every step: pinned host compact parameters -> H2D -> plan -> stepper (in-kernel control synthesis) -> "
                        "device NaN/silence/gain + PCM_24 quantisation -> D2H of output-u/-z/sum PCM (copy stream, overlapping the next step)"}
 
+    sweep = None
+    if a.sweep:
+        del out
+        torch.cuda.empty_cache()
+        sweep = run_sweep(a, [int(x) for x in a.sweep.split(",") if x], rank, world, dev)
+    drop_in = None
+    if rank == 0 and not a.no_drop_in:
+        try:
+            drop_in = run_drop_in(a, dev)
+        except Exception as e:                                          # diagnostics leg: never takes the headline down
+            drop_in = {"error": str(e)[:200]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -403,6 +520,7 @@ def main():
         "grid_point_updates_per_s": world * gpu_upd / per_step,
         "mean_operator_widths": {"W_t": Wt_mean, "W_l": Wl_mean},
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e,
+        "drop_in": drop_in, "sweep": sweep,
         "gpu_launches": int(launches), "clocks": clk, "step_ms": [round(x, 2) for x in step_ms],
         "peak_device_memory_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
         "health": {"status_bits": status, "nan_strings": nan_strings,

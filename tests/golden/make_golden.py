@@ -18,6 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, HERE)
 
 import ref_driver  # noqa: E402
 
@@ -25,64 +26,7 @@ sim, ext = ref_driver.import_reference()
 import torch  # noqa: E402
 import src.utils.fdm as fdm  # noqa: E402
 
-SR = 48000
-
-NSYNTH = dict(
-    sr=SR, f0_inf=98.0, alpha_inf=1, lambda_c=1, relative_order=4, theta=("auto", 0.03, 98.0),
-    string_kwargs=dict(
-        sampling_f0='random', sampling_kappa='random', sampling_alpha='random',
-        sampling_pickup='random', sampling_T60='random', precorrect=True,
-        f0_min=98.0, f0_max=440.0, f0_diff_max=30, f0_mod_max=0.08,
-        kappa_min=0.01, kappa_max=0.03, alpha_min=1., alpha_max=25.,
-        t60_min_1=10., t60_max_1=25., t60_min_2=10., t60_max_2=30.,
-        sampling_p_a='random', p_a_max=0.02, sampling_p_x='random', p_x_max=0.5),
-    hammer_kwargs=dict(M_r_min=1.0, M_r_max=10., alpha_fixed=3),
-    bow_kwargs=dict(),
-)
-
-ALLFIXED = dict(
-    sr=SR, f0_inf=55.0, alpha_inf=20, lambda_c=1, relative_order=8, theta=("auto", 0.08, 55.0),
-    string_kwargs=dict(
-        sampling_f0='fix', sampling_kappa='fix', sampling_alpha='fix',
-        sampling_pickup='fix', sampling_T60='fix', precorrect=True,
-        f0_fixed=55.0, kappa_fixed=0.08, alpha_fixed=20., lossless=False,
-        sampling_p_a='fix', p_a_fixed=0.02, sampling_p_x='fix', p_x_fixed=0.2),
-    hammer_kwargs=dict(x_H_min=0.1, x_H_max=0.1, v_H_min=4.0, v_H_max=4.0, M_r_min=1.5, M_r_max=1.5,
-                       w_H_min=2000, w_H_max=2000),
-    bow_kwargs=dict(x_b_min=0.2, x_b_max=0.2, v_b_min=0.35, v_b_max=0.35, F_b_min=90, F_b_max=90.,
-                    phi_0_max=9., phi_0_min=9., phi_1_max=0.01, phi_1_min=0.01, wid_min=4, wid_max=4),
-)
-
-LINEAR = dict(
-    sr=SR, f0_inf=55.0, alpha_inf=1, lambda_c=1, relative_order=8, theta=("auto", 0.03, 55.0),
-    string_kwargs=dict(
-        sampling_f0='fix', sampling_kappa='fix', sampling_alpha='fix',
-        sampling_pickup='random', sampling_T60='fix', precorrect=False,
-        f0_fixed=55.0, f0_mod_max=0, lossless=False, t60_fixed=20., kappa_min=0.03, kappa_max=0.03,
-        kappa_fixed=0.03, alpha_fixed=1., alpha_min=1., alpha_max=1.,
-        sampling_p_a='fix', p_a_fixed=0.01, sampling_p_x='fix', p_x_fixed=0.3, pluck_profile='smooth'),
-    hammer_kwargs=dict(x_H_min=0.5, x_H_max=0.5, v_H_min=2.5, v_H_max=2.5, M_r_min=10., M_r_max=10.,
-                       w_H_min=3000, w_H_max=3000, alpha_fixed=3),
-    bow_kwargs=dict(),
-)
-
-# hammered string with tension modulation on a finer grid (BASELINE config 4, scaled down)
-FINEHAMMER = dict(
-    sr=96000, f0_inf=55.0, alpha_inf=3, lambda_c=1, relative_order=8, theta=("auto", 0.01, 55.0),
-    string_kwargs=dict(
-        sampling_f0='fix', sampling_kappa='fix', sampling_alpha='fix',
-        sampling_pickup='random', sampling_T60='fix', precorrect=False,
-        f0_fixed=55.0, f0_mod_max=0, lossless=False, t60_fixed=20., kappa_fixed=0.01, alpha_fixed=3.,
-        sampling_p_a='fix', p_a_fixed=0.01, sampling_p_x='fix', p_x_fixed=0.25, pluck_profile='smooth'),
-    hammer_kwargs=dict(x_H_min=0.3, x_H_max=0.3, v_H_min=2.5, v_H_max=2.5, M_r_min=10., M_r_max=10.,
-                       w_H_min=3000, w_H_max=3000, alpha_fixed=3),
-    bow_kwargs=dict(),
-)
-
-# BASELINE config 4 at its stated rate: 192 kHz (N_t = 237, N_l = 593 with pre-correction off)
-FINEHAMMER192 = dict(FINEHAMMER, sr=192000)
-
-PRESETS = dict(nsynth=NSYNTH, allfixed=ALLFIXED, linear=LINEAR, finehammer=FINEHAMMER, finehammer192=FINEHAMMER192)
+from presets import *  # noqa: F401,F403  (SR, NSYNTH, ALLFIXED, LINEAR, FINEHAMMER*, PRESETS)
 
 CASES = dict(
     pluck_b1=dict(preset='nsynth', model='pluck', B=1, length=0.01),
@@ -97,6 +41,11 @@ CASES = dict(
     allfixed_pluck_b1=dict(preset='allfixed', model='pluck', B=1, length=0.01),
     manufactured_b1=dict(preset='linear', model='pluck', B=1, length=0.005, manufactured=True, chunk_length=0.001),
     finehammer_b1=dict(preset='finehammer', model='hammer', B=1, length=0.002),
+    # the same physical time (10 ms) on three more grids: observed order of accuracy against the analytic solution
+    manufactured_sr12k=dict(preset='linear12', model='pluck', B=1, length=0.01, manufactured=True, full_state=True),
+    manufactured_sr24k=dict(preset='linear24', model='pluck', B=1, length=0.01, manufactured=True, full_state=True),
+    manufactured_sr48k=dict(preset='linear', model='pluck', B=1, length=0.01, manufactured=True, full_state=True),
+    manufactured_sr96k=dict(preset='linear96', model='pluck', B=1, length=0.01, manufactured=True, full_state=True),
     pluck_b24=dict(preset='nsynth', model='pluck', B=24, length=0.004),
     random_b24=dict(preset='nsynth', model='random', B=24, length=0.004, seed=3),
     pluck_b2_long=dict(preset='nsynth', model='pluck', B=2, length=0.1, seed=5),

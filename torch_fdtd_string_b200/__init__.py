@@ -13,9 +13,9 @@ import os as _os
 # queues those streams alias and serialise.  Only effective when set before the CUDA context is created.
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
-from .forward_fn import (forward_fn, step_strings, build_args, Plan, synth_controls, postprocess,  # noqa: F401
+from .forward_fn import (forward_fn, step_strings, build_args, Plan, synth_controls, postprocess, deferred_checks,  # noqa: F401
                          make_xax, launch_count)
 from .simulate import process  # noqa: F401
 
-__all__ = ["forward_fn", "process", "step_strings", "build_args", "Plan", "synth_controls", "postprocess", "make_xax",
+__all__ = ["forward_fn", "process", "step_strings", "build_args", "Plan", "synth_controls", "postprocess", "deferred_checks", "make_xax",
            "launch_count"]

@@ -1,20 +1,28 @@
-"""Dataset generation on top of the B200 stepper: the part of the reference's ``run()`` that sits directly
-downstream of the time stepper (reference src/task/simulate.py:272-455, src/utils/misc.py:235-299,
-src/utils/audio.py:11-76) -- NaN / silence filtering, l-infinity normalisation, and the per-string result layout
+"""Dataset generation on top of the B200 stepper: the part of the reference's ``run()`` that sits directly up- and
+downstream of the time stepper (reference src/task/simulate.py:219-455, src/utils/misc.py:235-299,
+src/utils/audio.py:11-76) -- parameter draws, NaN / silence filtering, l-infinity normalisation, PCM quantisation and the
+per-string result layout
 
     {save_dir}/{id}-{b}/output-u.wav  output-z.wav  output.wav      (PCM_24 for double precision, PCM_16 for single)
     {save_dir}/{id}-{b}/simulation.npz  string_params.npz  hammer_params.npz  bow_params.npz  simulation_config.yaml
 
-with the reduction work (NaN mask, RMS, peak, gain) done on the device so that only the audio that is kept crosses
-PCIe.  Parameters come from the compact nsynth-like sampler (``sampler.py``); whole batches are sharded over ranks
+with everything per-sample done on the device (``sfdtd_postprocess``: NaN mask, RMS, peak, gain, PCM), so that only the
+audio and the arrays of strings that are KEPT cross PCIe.  Whole batches are sharded over ranks
 (``parallel.rank_batches``) -- one process per GPU, no collective.
 
-    python -m torch_fdtd_string_b200.dataset --save-dir out --num-samples 100 [--batch-size 24] [--excitation pluck]
+Two parameter sources:
+  * ``reference_source`` (the CLI's default): the reference's own draws, RNG-stream compatible (``sampler_ref.py``) --
+    ``proc.seed`` gives the reference's dataset.  The stream is sequential over batches, so every rank draws all batches
+    and keeps its share.
+  * ``native_source``: the compact nsynth-like sampler with one generator per batch index (``sampler.py``).
 
-Differences from the reference, all deliberate: ``simulation.npz`` does not hold ``state_u`` / ``state_z`` (the reference
-keeps the full (Nt, Nx) history of every string on the host: 21 MB per string-second; the drop-in ``forward_fn`` /
-``process`` path still produces it); no plots; ids are the batch index or 8 random characters per batch
-(``--randomize-name``) like the reference.
+``full_layout=True`` (reference-faithful, the CLI's default) also stores what makes the reference's files large: the
+state histories ``state_u[:, :max N_t + 1]`` / ``state_z[:, :max N_l + 1]`` in ``simulation.npz`` and the (Nt, Nx) initial
+displacement / velocity arrays in ``string_params.npz`` (src/task/simulate.py:405-408, src/utils/misc.py:241-251): the
+stepper then runs in the reference's (B, Nt, Nx) layout (``SFDTD_SAVE_STATE``), ~20 MB per string-second.  With
+``full_layout=False`` the archives hold the audio, the per-step outputs and the parameters only.
+
+    python -m torch_fdtd_string_b200.dataset --save-dir out --num-samples 100 [--batch-size 24] [--excitation pluck]
 """
 import argparse
 import os
@@ -24,17 +32,18 @@ import numpy as np
 import torch
 import yaml
 
-from . import sampler
+from . import sampler, sampler_ref
+from .forward_fn import Plan, build_args, postprocess as pcm_postprocess, synth_controls
 from .parallel import rank_batches
-from .wavio import write_wav
+from .wavio import write_wav_pcm
 
 _CHARS = np.array(list(_string.ascii_lowercase + _string.digits))
 
 
 def postprocess(uout, zout, silence_threshold=-23.0, normalize_output=True):
-    """Device-side reductions of reference src/task/simulate.py:333-335 and src/utils/audio.py:42-76.
-    uout, zout: (B, Nt-2) CUDA tensors.  Returns dict(is_nan, is_silent, gain (B,1), u, z, w) -- u/z/w are the
-    signals that go to the wav files (normalised by the l-infinity gain of ``uout`` when requested)."""
+    """PyTorch restatement of reference src/task/simulate.py:333-335 and src/utils/audio.py:42-76 (kept for tests and for
+    callers that want float signals; the generation path uses the fused device kernel ``sfdtd_postprocess``).
+    uout, zout: (B, Nt-2) CUDA tensors.  Returns dict(is_nan, is_silent, gain (B,1), u, z, w)."""
     is_nan = torch.isnan(uout.sum(-1))
     u = uout * (~is_nan).unsqueeze(-1)                       # NaN * 0 stays NaN, like the reference's multiply
     rms = u.pow(2).mean(-1, keepdim=True).pow(0.5)
@@ -69,22 +78,42 @@ def save_simulation_data(directory, excitation_type, simulation_dict, string_dic
         yaml.dump(short, f, default_flow_style=False)
 
 
-def _write_string(d, wavs, sr, bitrate, save, kinds, sim, string_dict, hammer_dict, bow_dict, theta_t, lambda_c):
+def _write_string(d, pcm, sr, bits, save, kinds, sim, string_dict, hammer_dict, bow_dict, theta_t, lambda_c):
     os.makedirs(d, exist_ok=True)
-    for name, x in zip(("output-u.wav", "output-z.wav", "output.wav"), wavs):
-        write_wav(f"{d}/{name}", x, sr, bitrate)
+    for name, raw in zip(("output-u.wav", "output-z.wav", "output.wav"), pcm):
+        write_wav_pcm(f"{d}/{name}", raw, sr, bits)
     if save:
         save_simulation_data(d, kinds, sim, string_dict, hammer_dict, bow_dict, theta_t, lambda_c)
+
+
+# ---- parameter sources: callables  it -> compact batch (CPU), called for it = 0, 1, 2, ... in order ------------------
+def native_source(batch_size, sr, length, excitation, seed, cfg=None):
+    """one generator per batch index: the result does not depend on the sharding"""
+    def draw(it):
+        return sampler.sample_nsynth_like(batch_size, sr=sr, length=length, excitation=excitation, seed=seed + it, cfg=cfg)
+    draw.sequential = False
+    return draw
+
+
+def reference_source(batch_size, sr, length, excitation, theta_t, f0_inf, alpha_inf, lambda_c, precision="double",
+                     string_kwargs=None, bow_kwargs=None, hammer_kwargs=None, manufactured=False, relative_order=4):
+    """the reference's draws from the GLOBAL torch RNG (seed it like reference run.py:75 first); must be called for every
+    batch index in order, on every rank"""
+    def draw(it):
+        return sampler_ref.sample_reference(batch_size, excitation, sr, length, theta_t, f0_inf, alpha_inf, lambda_c, precision,
+                                            string_kwargs, bow_kwargs, hammer_kwargs, manufactured, relative_order)
+    draw.sequential = True
+    return draw
 
 
 def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000, length=1.0, seed=1234,
              precision="double", normalize_output=True, skip_silence=True, silence_threshold=-23.0, save=True,
              randomize_name=False, batches_per_call=64, rank=0, world_size=1, device=None, surface_integral=True,
-             sampler_cfg=None, time_log=False, num_workers=4):
+             sampler_cfg=None, time_log=False, num_workers=4, source=None, full_layout=False, manufactured=False):
     """Generates ``num_samples // batch_size`` reference batches (reference run.py:109) and writes the kept strings.
-    The per-string files (three wavs, four compressed archives: ~0.3 s of zlib per string on one core, 3000x what the
-    stepper needs for that string) are written by ``num_workers`` threads (``proc.num_workers`` of the reference's config; zlib
-    releases the GIL) while the GPU runs the next call; at most two calls' host arrays are alive.
+    The per-string files (three wavs, four compressed archives: ~0.3 s of zlib per string on one core) are written by
+    ``num_workers`` threads (``proc.num_workers`` of the reference's config; zlib releases the GIL) while the GPU runs the
+    next call; at most two calls' host arrays are alive.
     Returns dict(strings, written, nan, silent, seconds_stepper, seconds_total)."""
     import concurrent.futures
     import time
@@ -94,17 +123,34 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     n_batches = num_samples // batch_size
     mine = list(rank_batches(n_batches, world_size, rank))
-    bitrate = "PCM_24" if precision == "double" else "PCM_16"
+    bits = 24 if precision == "double" else 16
     stats = dict(strings=0, written=0, nan=0, silent=0, seconds_stepper=0.0)
     rng = np.random.RandomState(seed + 7919 * rank)
     os.makedirs(save_dir, exist_ok=True)
+    if source is None:
+        source = native_source(batch_size, sr, length, excitation, seed, sampler_cfg)
+    drawn = {}
+    if getattr(source, "sequential", False):
+        for it in range(n_batches):                    # the stream is sequential: draw every batch, keep this rank's
+            q = source(it)
+            if it in mine:
+                drawn[it] = q
+    if full_layout:
+        # (B, Nt, Nx) histories on the device: bound a call to ~48 GB of state
+        Nt_ = int(sr * length)
+        q0 = drawn[mine[0]] if drawn else (source(mine[0]) if mine else None)
+        if q0 is not None:
+            per_batch = batch_size * Nt_ * (q0["Nx_t1"] + q0["Nx_l1"]) * 8
+            batches_per_call = max(1, min(batches_per_call, int(48e9 // max(per_batch, 1))))
+            if not drawn:
+                drawn[mine[0]] = q0
     calls, names = [], {}
     for c0 in range(0, len(mine), batches_per_call):
-        # one sampler stream per batch index, so that the result does not depend on the sharding; batches of one call must
-        # share the padded state widths (they come from the batch's largest stiffness, like in the reference)
+        # batches of one call must share the padded state widths (they come from the batch's largest stiffness, like in
+        # the reference)
         by_width = {}
         for it in mine[c0:c0 + batches_per_call]:
-            q = sampler.sample_nsynth_like(batch_size, sr=sr, length=length, excitation=excitation, seed=seed + it, cfg=sampler_cfg)
+            q = drawn.pop(it) if it in drawn else source(it)
             by_width.setdefault((q["Nx_t1"], q["Nx_l1"]), []).append((it, q))
         calls += list(by_width.values())
     for group in calls:
@@ -112,35 +158,52 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
         B = len(chunk) * batch_size
         p_host = sampler.concat([q for _, q in group])
         p = sampler.to_device(p_host, device)
-        ctl = sampler.expand_controls(p, device)
+        Nt = p_host["Nt"]
+        f64 = dict(dtype=torch.float64, device=device)
+        if full_layout:
+            su = torch.zeros(B, Nt, p_host["Nx_t1"], **f64); su[:, :2] = p["state_u"]
+            sz = torch.zeros(B, Nt, p_host["Nx_l1"], **f64); sz[:, :2] = p["state_z"]
+        else:
+            su, sz = p["state_u"].clone(), p["state_z"].clone()
+        args, res, keep_alive = build_args(
+            su, sz, kappa=p["kappa"], alpha=p["alpha"], pos=p["pos"], T60=p["T60"], phi_0=p["phi_0"], phi_1=p["phi_1"],
+            x_H=p["x_H"], w_H=p["w_H"], M_r=p["M_r"], alpha_H=p["alpha_H"], bow_mask=p["bow_mask"], hammer_mask=p["hammer_mask"],
+            k=p_host["k"], theta_t=p_host["theta_t"], lambda_c=p_host["lambda_c"], relative_order=p_host["relative_order"],
+            Nt=Nt, group_size=batch_size, synth=sampler.synth_dict(p), surface_integral=surface_integral,
+            save_state=full_layout, manufactured=manufactured, p_a=p["p_a"])
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        plan = Plan(args)
         e0.record()
-        res = sampler.run_compact(p, batch_size, surface_integral=surface_integral, controls=ctl)
+        plan.run(args)
         e1.record()
-        uout, zout = res["uout"][:, 2:], res["zout"][:, 2:]
-        pp = postprocess(uout, zout, silence_threshold, normalize_output)
-        torch.cuda.synchronize()
+        plan.close()
+        pp = pcm_postprocess(res["uout"], res["zout"], n0=2, silence_db=silence_threshold, normalize=normalize_output, bits=bits)
+        is_nan = pp["is_nan"].cpu().numpy().astype(bool); is_silent = pp["is_silent"].cpu().numpy().astype(bool)     # (synchronises)
         stats["seconds_stepper"] += e0.elapsed_time(e1) * 1e-3
         if time_log:
             # reference src/task/simulate.py:327-328 logs one line per batch; here one stepper call covers several batches
             with open(f"{save_dir}/gpu_time.txt", "a") as f:
                 for it in chunk:
                     f.write(f"{it}\t{e0.elapsed_time(e1) * 1e-3 / len(chunk):.4f}\n")
-        is_nan = pp["is_nan"].cpu().numpy(); is_silent = pp["is_silent"].cpu().numpy()
         keep = ~is_nan & ~(is_silent & skip_silence)
         stats["strings"] += B; stats["nan"] += int(is_nan.sum()); stats["silent"] += int((is_silent & ~is_nan).sum())
         if not keep.any():
             continue
-        idx = torch.from_numpy(np.nonzero(keep)[0]).to(device)
-        host = {k: pp[k].index_select(0, idx).cpu().numpy() for k in ("u", "z", "w")}       # only kept audio crosses PCIe
+        kept = np.nonzero(keep)[0]
+        idx = torch.from_numpy(kept).to(device)
+        row = pp["row_bytes"]
+        pcm = {k: pp["pcm_" + k].index_select(0, idx)[:, :row].cpu().numpy() for k in ("u", "z", "w")}   # only kept audio crosses PCIe
         raw = {k: res[k].index_select(0, idx)[:, 2:].cpu().numpy() for k in ("uout", "zout", "v_r", "F_H", "u_H_out")}
-        f0 = ctl["f0"].index_select(0, idx).cpu().numpy()
-        ctl_h = {k: ctl[k].index_select(0, idx).cpu().numpy() for k in ("x_b", "v_b", "F_b", "u_H")}
+        sub = {k: (v.index_select(0, idx) if isinstance(v, torch.Tensor) and v.dim() > 0 and v.size(0) == B else v) for k, v in p.items()}
+        ctl = synth_controls(sampler.synth_dict(sub), len(kept), Nt, device)                  # the curves the stepper used
+        ctl_h = {k: ctl[k].cpu().numpy() for k in ("f0", "x_b", "v_b", "F_b", "u_H")}
+        f0 = ctl_h["f0"]
         sig0 = res["sig0"].cpu().numpy(); sig1 = res["sig1"].cpu().numpy()
         nt_, nl_ = sampler.derived_grid(torch.from_numpy(f0), p_host["kappa"][keep].view(-1, 1), p_host["k"], p_host["theta_t"],
                                         p_host["lambda_c"], p_host["alpha"][keep].view(-1, 1))
+        w0 = sampler.fletcher_w0(p_host["kappa"])
         new_jobs = []
-        for j, b in enumerate(np.nonzero(keep)[0]):
+        for j, b in enumerate(kept):
             it = chunk[b // batch_size]; bb = b % batch_size
             if it not in names:
                 names[it] = "".join(rng.choice(_CHARS, 8)) if randomize_name else str(it)
@@ -149,22 +212,37 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
             bow, ham = bool(p_host["bow_mask"][b]), bool(p_host["hammer_mask"][b])
             kinds = (["bow"] if bow else []) + (["hammer"] if ham else []) + (["pluck"] if not (bow or ham) else [])
             sim = dict(uout=raw["uout"][j], zout=raw["zout"][j], v_r_out=raw["v_r"][j], F_H_out=raw["F_H"][j],
-                       u_H_out=raw["u_H_out"][j], bow_mask=bow, hammer_mask=ham, pluck_mask=not (bow or ham),
-                       Nx_t=nt_[j].numpy(), Nx_l=nl_[j].numpy(), sig0=sig0[b], sig1=sig1[b])
+                       u_H_out=raw["u_H_out"][j], bow_mask=np.array([[bow]]), hammer_mask=np.array([[ham]]),
+                       pluck_mask=np.array([[not (bow or ham)]]), Nx_t=nt_[j].numpy(), Nx_l=nl_[j].numpy(),
+                       sig0=sig0[b], sig1=sig1[b])
             T = lambda key: p_host[key][b].numpy()
-            string_dict = dict(kappa=T("kappa"), alpha=T("alpha"), u0=p_host["state_u"][b, 1].numpy(),
-                               v0=np.zeros_like(p_host["state_u"][b, 1].numpy()), p_a=T("p_a"), f0=f0[j], pos=T("pos"),
-                               T60=T("T60"), target_f0=f0[j] * float(sampler.fletcher_w0(p_host["kappa"][b])))
-            hammer_dict = dict(x_H=T("x_H"), v_H=T("v_H"), u_H=ctl_h["u_H"][j], w_H=T("w_H"), M_r=T("M_r"), alpha=T("alpha_H"))
+            u0_row = p_host["state_u"][b, 1].numpy()
+            if full_layout:
+                # reference layout (src/task/simulate.py:405-408): histories trimmed to the largest grid of the string
+                sim["state_u"] = su[b, :, :int(nt_[j].max()) + 1].cpu().numpy()
+                sim["state_z"] = sz[b, :, :int(nl_[j].max()) + 1].cpu().numpy()
+                u0 = np.zeros((Nt, u0_row.size)); u0[0] = p_host["state_u"][b, 0].numpy()
+                v0 = np.zeros_like(u0)
+                v_H = np.zeros(Nt); v_H[1] = float(p_host["v_H"][b])
+            else:
+                u0, v0, v_H = u0_row, np.zeros_like(u0_row), T("v_H")
+            tf = f0[j] * float(w0[b]) if p_host.get("target_f0_a") is None else None
+            if tf is None:
+                q1 = {k: p_host[k][b:b + 1] for k in ("mod_frq", "mod_amp", "vib_t0")}
+                q1["f0_a"] = p_host["target_f0_a"][b:b + 1]; q1["f0_b"] = p_host["target_f0_b"][b:b + 1]
+                tf = sampler._f0_curve(q1, Nt, p_host["k"], torch.arange(1, Nt + 1, dtype=torch.float64).view(1, -1))[0].numpy()
+            string_dict = dict(kappa=T("kappa"), alpha=T("alpha"), u0=u0, v0=v0, p_a=np.array([[float(p_host["p_a"][b])]]),
+                               f0=f0[j], pos=T("pos"), T60=T("T60"), target_f0=tf)
+            hammer_dict = dict(x_H=T("x_H"), v_H=v_H, u_H=ctl_h["u_H"][j], w_H=T("w_H"), M_r=T("M_r"), alpha=T("alpha_H"))
             bow_dict = dict(x_B=ctl_h["x_b"][j], v_B=ctl_h["v_b"][j], F_B=ctl_h["F_b"][j], phi_0=T("phi_0"), phi_1=T("phi_1"),
-                            wid_B=T("wid"))
-            new_jobs.append(pool.submit(_write_string, d, (host["u"][j], host["z"][j], host["w"][j]), sr, bitrate, save,
+                            wid_B=np.full(Nt, float(p_host["wid"][b])) if full_layout else T("wid"))
+            new_jobs.append(pool.submit(_write_string, d, (pcm["u"][j], pcm["z"][j], pcm["w"][j]), sr, bits, save,
                                         ",".join(kinds), sim, string_dict, hammer_dict, bow_dict, p_host["theta_t"], p_host["lambda_c"]))
             stats["written"] += 1 if save else 0
         for fut in pending:                     # the previous call's files must be on disk before a third call's arrays pile up
             fut.result()
         pending = new_jobs
-        del res, ctl, pp
+        del res, ctl, pp, su, sz, args, keep_alive
     for fut in pending:
         fut.result()
     pool.shutdown()
@@ -185,13 +263,14 @@ def main():
     ap.add_argument("--no-normalize", action="store_true")
     ap.add_argument("--keep-silent", action="store_true")
     ap.add_argument("--randomize-name", action="store_true")
+    ap.add_argument("--full-layout", action="store_true", help="also store the state histories and (Nt, Nx) initial arrays like the reference")
     ap.add_argument("--num-workers", type=int, default=4, help="file-writer threads (proc.num_workers of the reference's config)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     st = generate(a.save_dir, a.num_samples, a.batch_size, a.excitation, a.sr, a.length, a.seed, a.precision,
                   not a.no_normalize, not a.keep_silent, randomize_name=a.randomize_name, rank=rank, world_size=world,
-                  num_workers=a.num_workers)
+                  num_workers=a.num_workers, full_layout=a.full_layout)
     print(st)
 
 

@@ -260,6 +260,33 @@ def postprocess(uout, zout, n0=2, n_samples=None, silence_db=-23.0, normalize=Tr
     return res
 
 
+class deferred_checks:
+    """Context manager: inside it ``forward_fn`` does not read the status words back (its only host synchronisation after
+    the launch), so several reference batches can be in flight on several streams; the statuses are checked on exit.
+
+        with deferred_checks():
+            for s, args in zip(streams, batches):
+                with torch.cuda.stream(s):
+                    outs.append(forward_fn(*args))
+    """
+    active = False
+    pending = []
+
+    def __enter__(self):
+        deferred_checks.active = True
+        deferred_checks.pending = []
+        return self
+
+    def __exit__(self, *exc):
+        deferred_checks.active = False
+        pend, deferred_checks.pending = deferred_checks.pending, []
+        if exc[0] is None:
+            torch.cuda.synchronize()
+            for st in pend:
+                _check_status(st)
+        return False
+
+
 def forward_fn(state_u, state_z, string_params, bow_params, hammer_params,
                bow_mask, hammer_mask, constant, relative_error,
                surface_integral, manufactured, n_0, Nt):
@@ -302,7 +329,9 @@ def forward_fn(state_u, state_z, string_params, bow_params, hammer_params,
         bow_mask=bow_mask, hammer_mask=hammer_mask,
         k=constant[0], theta_t=constant[1], lambda_c=constant[2], relative_order=relative_error,
         Nt=Nt, group_size=B, surface_integral=bool(surface_integral), save_state=True, manufactured=bool(manufactured), n_0=n_0,
-        p_a=D(p_a))
+        p_a=D(p_a), check=not deferred_checks.active)
+    if deferred_checks.active:
+        deferred_checks.pending.append(res["status"])
     # in-place side effects of the reference (string.cpp:264-265, 303)
     if su_cp: state_u.copy_(su)
     if sz_cp: state_z.copy_(sz)

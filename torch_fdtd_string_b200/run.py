@@ -13,7 +13,12 @@ reference's result-file layout (``dataset.py``).
 Under ``torchrun`` every rank takes its share of the batches (``proc.gpus`` is ignored then); otherwise the first entry of
 ``proc.gpus`` selects the device.  What the reference's CLI can do and this one refuses, loudly: ``proc.cpu=true`` (there is
 no CPU path), ``proc.{evaluate,summarize,process_training_data,train,test}`` (not part of the time-stepping path),
-``sampling_*: equidist``, ``task.load_config``, ``task.plot`` / ``plot_state`` (ignored with a notice).
+``task.load_config``, ``task.plot`` / ``plot_state`` (ignored with a notice).
+
+Parameters are drawn by ``sampler_ref`` -- the reference's String / Bow / Hammer draws restated RNG-stream compatibly, so
+``proc.seed`` reproduces the reference's dataset (all sampling modes, pluck profiles, the manufactured initial condition).
+``SFDTD_SAMPLER=native`` selects the per-batch-seeded compact sampler instead; ``SFDTD_COMPACT_RESULTS=1`` leaves the state
+histories and the (Nt, Nx) initial arrays out of the archives (the reference always stores them: ~20 MB per string-second).
 """
 import os
 import shutil
@@ -91,6 +96,32 @@ def sampler_config(task):
     c.update(f0_inf=float(task["f0_inf"]), alpha_inf=float(task["alpha_inf"]), lambda_c=float(task["lambda_c"]),
              relative_order=task["relative_order"], theta_t=task.get("theta_t"))
     return c
+
+
+def reference_kwargs(task):
+    """task node -> (string_kwargs, hammer_kwargs, bow_kwargs, theta_t) exactly as reference run() builds them
+    (src/task/simulate.py:224-267)"""
+    def first(lst, key):
+        for item in lst or []:
+            if key in item:
+                return item[key]
+        raise H.ConfigError(f"Specify '{key}' for task.string_condition")
+    sc = task.get("string_condition")
+    kappa_max = first(sc, "kappa_fixed") if task.get("sampling_kappa") == "fix" else first(sc, "kappa_max")
+    f0_min = first(sc, "f0_fixed") if task.get("sampling_f0") == "fix" else first(sc, "f0_min")
+    from . import sampler
+    theta_t = sampler.get_theta(kappa_max, f0_min, task["sr"]) if task.get("theta_t") is None else task["theta_t"]
+    sk = {k: ("random" if task.get(k) is None else task.get(k))
+          for k in ("sampling_f0", "sampling_kappa", "sampling_alpha", "sampling_pickup", "sampling_T60", "precorrect")}
+
+    def upd(dst, lst):
+        for item in lst or []:
+            (key, val), = item.items()
+            if val is not None:
+                dst[key] = val
+        return dst
+    upd(sk, sc); upd(sk, task.get("pluck_condition"))
+    return sk, upd({}, task.get("hammer_condition")), upd({}, task.get("bow_condition")), theta_t
 
 
 def print_config(cfg, path="config_tree.txt"):
@@ -206,9 +237,6 @@ def main(argv=None):
     if proc.get("simulate"):
         if rank == 0:
             backup_code()
-        if task.get("manufactured"):
-            raise NotImplementedError("task.manufactured=true: the manufactured-solution mode is reachable through "
-                                      "forward_fn(..., manufactured=True); the dataset driver does not sample it")
         if task.get("load_config") is not None:
             raise NotImplementedError("task.load_config (npy parameter dumps) is not built")
         for key in ("plot", "plot_state"):
@@ -218,13 +246,23 @@ def main(argv=None):
             raise RuntimeError("no CUDA device: this package has no CPU path")
         torch.cuda.set_device(device_index)
         from . import dataset
+        # parameter draws: the reference's own, RNG-stream compatible (proc.seed gives the reference's dataset); set
+        # SFDTD_SAMPLER=native for the per-batch-seeded compact sampler
+        source = None
+        if os.environ.get("SFDTD_SAMPLER", "reference") == "reference":
+            sk, hk, bk, theta_t = reference_kwargs(task)
+            source = dataset.reference_source(
+                int(task["batch_size"]), int(task["sr"]), float(task["length"]), p["model_name"], theta_t, task["f0_inf"],
+                task["alpha_inf"], task["lambda_c"], task["precision"], sk, bk, hk, bool(task.get("manufactured")),
+                task["relative_order"])
         stats = dataset.generate(
             p["save_dir"], int(task["num_samples"]), int(task["batch_size"]), p["model_name"], int(task["sr"]),
             float(task["length"]), int(proc["seed"]), task["precision"], bool(task["normalize_output"]),
             bool(task["skip_silence"]), float(task["silence_threshold"]), save=bool(task.get("save", True)),
             randomize_name=bool(task["randomize_name"]), rank=rank, world_size=world,
-            surface_integral=bool(task["surface_integral"]), sampler_cfg=sampler_config(task),
-            time_log=True, num_workers=int(proc.get("num_workers") or 1))
+            surface_integral=bool(task["surface_integral"]), sampler_cfg=(sampler_config(task) if source is None else None),
+            time_log=True, num_workers=int(proc.get("num_workers") or 1), source=source,
+            full_layout=os.environ.get("SFDTD_COMPACT_RESULTS", "0") != "1", manufactured=bool(task.get("manufactured")))
         print(f"[run] rank {rank}/{world}: {stats}")
     return 0
 

@@ -23,3 +23,13 @@ def write_wav(path, data, sr, subtype="PCM_16"):
         f.setsampwidth(width)
         f.setframerate(int(sr))
         f.writeframes(q)
+
+
+def write_wav_pcm(path, raw, sr, bits):
+    """mono wav from already quantised little-endian PCM bytes (what ``sfdtd_postprocess`` produces on the device):
+    ``raw`` = uint8 array of n_samples * bits/8 bytes"""
+    with wave.open(path, "wb") as f:
+        f.setnchannels(1)
+        f.setsampwidth(bits // 8)
+        f.setframerate(int(sr))
+        f.writeframes(np.ascontiguousarray(raw, dtype=np.uint8).tobytes())
