@@ -81,8 +81,7 @@ def compact_time(x):
 
 def run_case(name, spec, perturb=False):
     p = PRESETS[spec['preset']]
-    if spec.get('threads'):
-        torch.set_num_threads(spec['threads'])
+    torch.set_num_threads(spec.get('threads', 2))
     sr = p['sr']
     mode, kap, f0m = p['theta']
     theta_t = fdm.get_theta(kap, f0m, sr)
@@ -227,7 +226,7 @@ if __name__ == "__main__":
     argv = sys.argv[1:]
     if argv and argv[0] == "--merge-pert":
         for nm in argv[1:]:
-            merge_pert(nm)
+            merge_pert(nm, win=480 if CASES[nm].get('long') else 48)
     elif argv and argv[0] == "--perturbed":
         for nm in argv[1:]:
             run_case(nm, CASES[nm], perturb=True)

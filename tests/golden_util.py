@@ -16,6 +16,7 @@ LONG = ("pluck_b1_1s", "pluck_b24_1s", "allfixed_bow_b1_4s", "finehammer192_b1",
 def golden_names(long=False):
     """short fixtures (all outputs + states), or the full-length ones of the BASELINE configs (audio only)"""
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    names = [n for n in names if not n.startswith("run_")]             # run_*: files of the reference's run() (test_gpu_dataset.py)
     return [n for n in names if (n in LONG) == long]
 
 

@@ -11,10 +11,13 @@ import golden_util as gu
 pytestmark = pytest.mark.gpu
 
 KEYS = ["uout", "zout", "v_r_out", "F_H_out", "u_H_out"]
-TOL_U = 1e-6
-# fixtures that contain a string whose dynamics amplify 1-ulp perturbations exponentially in the
-# reference scheme itself (DESIGN.md "sensitivity"): the oracle-vs-reference distance is already 1e-8..1e-6
-TOL_SENSITIVE = {"pluck_b24": 1e-5, "pluck_b2_long": 1e-3}
+# Gate of the short fixtures: measured on B200 (round 2) every key of every fixture is <= 2.4e-10 except on the two
+# fixtures that contain strings the reference itself is sensitive on (below) -> 3e-8 (~100 x measured; north_star asks 1e-6).
+TOL_U = 3e-8
+# `pluck_b24` / `pluck_b2_long` contain strings whose dynamics amplify 1-ulp perturbations in the reference itself; they
+# carry the reference-vs-perturbed-reference distance (`pert_*`), and uout / zout are checked per string and window against
+# 100 x that distance (floor 3e-8); their other keys are checked on the strings that are calm in the reference.
+SENSITIVE = ("pluck_b24", "pluck_b2_long")
 NOT_BUILT = set()
 
 
@@ -34,32 +37,52 @@ def run_cuda(g, chunk=None):
 def test_cuda_matches_reference_golden(name):
     g = gu.load_golden(name)
     out, inp = run_cuda(g)
-    tol = TOL_SENSITIVE.get(name, TOL_U)
-    errs = {}
+    B = int(g["B"])
     for k in KEYS:
         assert tuple(out[k].shape) == g[k].shape, (k, out[k].shape, g[k].shape)
-        errs[k] = gu.rel_l2(out[k].cpu().numpy(), g[k])
-    errs["state_u_last"] = gu.rel_l2(out["state_u"][:, -2:, :].cpu().numpy(), g["state_u_last"])
-    errs["state_z_last"] = gu.rel_l2(out["state_z"][:, -2:, :].cpu().numpy(), g["state_z_last"])
+    calm = np.ones(B, dtype=bool)
+    if name in SENSITIVE and "pert_win" in g:
+        for key in ("uout", "zout"):
+            x = out[key].cpu().numpy(); r = g[key]
+            for b in range(B):
+                worst, tot, sens = _check_against_reference_sensitivity(g, key, b, x[b], r[b], floor=TOL_U)
+                print(f"{name} {key}[{b}] rel.L2 {tot:.2e} (reference vs itself {sens:.2e}) worst window err/bound {worst:.2f}")
+                assert worst <= 1.0, (name, key, b, worst)
+                if sens > 1e-12:
+                    calm[b] = False
+        assert calm.sum() >= B // 2
+    elif name in SENSITIVE:
+        pytest.skip("perturbed-reference data not merged into the fixture yet")
+    errs = {}
+    sel = np.nonzero(calm)[0]
+    for k in KEYS:
+        errs[k] = gu.rel_l2(out[k].cpu().numpy()[sel], g[k][sel])
+    errs["state_u_last"] = gu.rel_l2(out["state_u"][:, -2:, :].cpu().numpy()[sel], g["state_u_last"][sel])
+    errs["state_z_last"] = gu.rel_l2(out["state_z"][:, -2:, :].cpu().numpy()[sel], g["state_z_last"][sel])
     print(name, {k: f"{v:.2e}" for k, v in errs.items()})
     for k, v in errs.items():
-        assert v < (tol if k != "state_z_last" and k != "zout" else max(tol, 1e-5)), (name, k, v)
+        assert v < TOL_U, (name, k, v)
     np.testing.assert_allclose(out["sig0"].cpu().numpy().ravel(), g["sig0"].ravel(), rtol=1e-10)
-    assert gu.rel_l2(inp["hammer_params"][2].cpu().numpy(), g["u_H_inplace"]) < tol
+    assert gu.rel_l2(inp["hammer_params"][2].cpu().numpy()[sel], g["u_H_inplace"][sel]) < TOL_U
     if "state_u_full" in g:
-        assert gu.rel_l2(out["state_u"].cpu().numpy(), g["state_u_full"]) < tol
+        assert gu.rel_l2(out["state_u"].cpu().numpy()[sel], g["state_u_full"][sel]) < TOL_U
 
 
 # ---- the BASELINE configs at their stated length (fixtures: audio only, made by tests/golden/make_golden.py) ----------
-# measured relative L2 of the CUDA path against the unmodified reference (B200, this round) -> gate = 100 x measured,
-# never looser than the 1e-6 of north_star
+# Gate: 1e-6 relative L2 (north_star) over the whole run -- except where the REFERENCE ITSELF is more sensitive than that.
+# Its own sensitivity is measured, not assumed: the fixtures `pluck_b1_1s` / `pluck_b24_1s` carry the distance between the
+# unmodified reference and the unmodified reference run on state_u * (1 + 2^-50) (`pert_*`, per string and 10 ms window;
+# tests/golden/make_golden.py --perturbed / --merge-pert).  For the nsynth-like string of configs[0] that distance is
+# 4e-13 after 10 ms, 1e-6 after 60 ms and 1e-3 after 120 ms: the scheme amplifies one ulp by ~30x per 10 ms, so no
+# implementation (including the reference on another BLAS) can agree with it to 1e-6 over a second.  There the bound per
+# window is 100 x the reference's own distance (a solver that re-converges to 1e-13 every step injects ~100 ulp).
 FULL_LENGTH = {
-    # name: keys compared
-    "pluck_b1_1s": ("uout", "zout", "v_r_out", "F_H_out", "u_H_out"),          # configs[0]: 47 998 samples
     "finehammer192_b1": ("uout", "zout", "v_r_out", "F_H_out", "u_H_out"),     # configs[3] at 192 kHz: 9 598 samples, N_t = 237
     "allfixed_bow_b1_4s": ("uout", "zout", "v_r_out"),                         # configs[2]: 191 998 samples
 }
-FULL_LENGTH_GATE = {"pluck_b1_1s": 1e-6, "finehammer192_b1": 1e-6, "allfixed_bow_b1_4s": 1e-6}
+# measured on B200 this round (rel. L2 vs the reference): finehammer192_b1 uout 2.7e-10 zout 1.7e-10;
+# allfixed_bow_b1_4s see profiles/parity_r02.md -> gates at <= 100 x measured, never looser than 1e-6
+FULL_LENGTH_GATE = {"finehammer192_b1": 3e-8, "allfixed_bow_b1_4s": 1e-6}
 
 
 def _have(name):
@@ -85,13 +108,52 @@ def test_full_length_config_matches_reference(name):
         assert v < FULL_LENGTH_GATE[name], (name, k, v)
 
 
+def _check_against_reference_sensitivity(g, key, b, x, r, factor=100.0, floor=1e-6):
+    """x, r: one string's samples (CUDA, reference).  Per 10 ms window: relative L2 distance <= max(floor, factor x the
+    reference's own distance to its perturbed run).  Returns (worst ratio err / bound, total rel. L2, total bound)."""
+    win = int(g["pert_win"])
+    nw = min(len(r) // win, g[f"pert_{key}_err"].shape[1])
+    worst = 0.0
+    for w in range(nw):
+        sl = slice(w * win, (w + 1) * win)
+        nr = np.linalg.norm(r[sl])
+        if not np.isfinite(nr) or nr == 0 or not np.isfinite(x[sl]).all():
+            break
+        err = np.linalg.norm(x[sl] - r[sl]) / nr
+        sens = g[f"pert_{key}_err"][b, w] / max(g[f"pert_{key}_norm"][b, w], 1e-300)
+        worst = max(worst, err / max(floor, factor * sens))
+    n = nw * win
+    tot = np.linalg.norm(x[:n] - r[:n]) / np.linalg.norm(r[:n])
+    sens_tot = np.sqrt((g[f"pert_{key}_err"][b, :nw] ** 2).sum()) / np.sqrt((g[f"pert_{key}_norm"][b, :nw] ** 2).sum())
+    return worst, tot, sens_tot
+
+
+def test_single_string_full_length_within_reference_sensitivity():
+    """BASELINE configs[0]: single plucked nsynth-like string, 1 s @ 48 kHz, fp64, 47 998 samples."""
+    name = "pluck_b1_1s"
+    if not _have(name):
+        pytest.skip(f"fixture {name} not generated")
+    g = gu.load_golden(name)
+    out, _ = run_cuda(g)
+    for key in ("uout", "zout"):
+        x = out[key].cpu().numpy()[0]; r = g[key][0]
+        assert x.shape == r.shape and np.isfinite(x).all() and np.isfinite(r).all()
+        worst, tot, sens = _check_against_reference_sensitivity(g, key, 0, x, r)
+        first = np.linalg.norm(x[:480] - r[:480]) / np.linalg.norm(r[:480])
+        print(name, key, f"first 10 ms {first:.2e}; whole second {tot:.2e} (reference vs its own 1-ulp perturbation: {sens:.2e}); "
+              f"worst window err/bound {worst:.2f}")
+        assert first < 1e-9, (key, first)           # before the amplification sets in the paths agree to ~1e-12
+        assert worst <= 1.0, (key, worst)
+    for k in ("F_H_out", "u_H_out"):               # not fed by the chaotic displacement of an un-hammered string
+        assert gu.rel_l2(out[k].cpu().numpy(), g[k]) < 1e-9, k
+
+
 def test_nsynth_batch_full_length_nan_mask_and_per_string_parity():
     """BASELINE configs[1]: one nsynth-like reference batch (24 strings, 1 s @ 48 kHz, fp64) at full length.
     * the set of strings that blow up to NaN is the reference's, and they do so at (nearly) the same sample
       (reference src/task/simulate.py:91-93,333-334 drops them);
-    * every other string matches the reference per string: <= 1e-6 relative L2 over the whole second, except where the
-      REFERENCE ITSELF is more sensitive than that -- measured by running the unmodified reference on the same inputs with
-      state_u * (1 + 2^-50) (`pert_*` arrays of the fixture): there the bound is 100 x the reference's own distance."""
+    * every other string matches the reference per string and per 10 ms window: <= 1e-6 relative L2, except where the
+      reference itself is more sensitive (see above): there <= 100 x the reference's own distance."""
     name = "pluck_b24_1s"
     if not _have(name):
         pytest.skip(f"fixture {name} not generated")
@@ -104,33 +166,25 @@ def test_nsynth_batch_full_length_nan_mask_and_per_string_parity():
         bad_x, bad_r = ~np.isfinite(x), ~np.isfinite(r)
         nan_x, nan_r = bad_x.any(1), bad_r.any(1)
         on_x = np.where(nan_x, bad_x.argmax(1), -1); on_r = np.where(nan_r, bad_r.argmax(1), -1)
-        win = int(g["pert_win"]) if "pert_win" in g else 480
         for b in range(x.shape[0]):
             if nan_r[b] or nan_x[b]:
-                # NaN strings: same set; onset within the reference's own sensitivity window (its perturbed run's onset) or 10 ms
+                # NaN strings: same set; onset within the reference's own sensitivity (its perturbed run's onset) or 10 ms
                 assert nan_r[b] and nan_x[b], (key, b, "NaN mask differs", int(on_x[b]), int(on_r[b]))
                 slack = 480
-                if f"pert_{key}_nan_onset" in g and g[f"pert_{key}_nan_onset"][b] >= 0:
-                    slack = max(slack, 2 * abs(int(g[f"pert_{key}_nan_onset"][b]) - int(on_r[b])))
+                if g[f"pert_{key}_nan_onset"][b] >= 0:
+                    slack = max(slack, 3 * abs(int(g[f"pert_{key}_nan_onset"][b]) - int(on_r[b])))
                 assert abs(int(on_x[b]) - int(on_r[b])) <= slack, (key, b, int(on_x[b]), int(on_r[b]), slack)
-                n_ok = max(0, min(int(on_x[b]), int(on_r[b])) - 4800)      # compare up to 0.1 s before the blow-up
+                n_ok = max(0, min(int(on_x[b]), int(on_r[b])) - 480)
             else:
                 n_ok = x.shape[1]
-            if n_ok < win:
-                rep.append((key, b, "nan-early", None, None)); continue
-            err = np.linalg.norm(x[b, :n_ok] - r[b, :n_ok]) / np.linalg.norm(r[b, :n_ok])
-            tol = 1e-6
-            if f"pert_{key}_err" in g:
-                nw = n_ok // win
-                sens = np.sqrt((g[f"pert_{key}_err"][b, :nw] ** 2).sum()) / max(np.sqrt((g[f"pert_{key}_norm"][b, :nw] ** 2).sum()), 1e-300)
-                tol = max(tol, 100 * sens)
-            rep.append((key, b, "ok" if err < tol else "FAIL", float(err), float(tol)))
+            worst, tot, sens = _check_against_reference_sensitivity(g, key, b, x[b, :n_ok], r[b, :n_ok])
+            rep.append((key, b, "nan" if nan_r[b] else "ok", float(tot), float(sens), float(worst)))
     for row in rep:
-        print(row)
-    assert not [r for r in rep if r[2] == "FAIL"]
-    # most strings of the batch must meet the plain 1e-6 bound (the sensitive ones are a minority)
-    plain = [r for r in rep if r[0] == "uout" and r[3] is not None and r[3] < 1e-6]
-    assert len(plain) >= 12, len(plain)
+        print("%s[%2d] %-3s rel.L2 %.2e  (reference vs itself %.2e)  worst window err/bound %.2f" % row)
+    assert max(r[5] for r in rep) <= 1.0
+    # strings that are NOT sensitive in the reference must meet the plain 1e-6 bound over the whole run
+    calm = [r for r in rep if r[2] == "ok" and r[4] < 1e-8]
+    assert all(r[3] < 1e-6 for r in calm), [r for r in calm if r[3] >= 1e-6]
 
 
 def test_chunked_equals_unchunked_on_gpu():
@@ -182,7 +236,7 @@ def test_cuda_matches_oracle_on_seeded_groups(oracle, name, B):
     for k in KEYS:
         err = gu.rel_l2(res[m[k]][:, 2:].cpu().numpy(), ref[k])
         print(k, f"{err:.2e}")
-        assert err < (TOL_U if name != "pluck_b24" else 1e-5), (k, err)
+        assert err < (TOL_U if name != "pluck_b24" else 1e-5), (k, err)      # (pluck_b24: vs the ORACLE, which sits 1e-6 from the reference on its sensitive strings)
     cnt = res["counters"].cpu().numpy()
     assert (cnt[:, 3] == Nt - 2).all()
 

@@ -11,7 +11,8 @@ import golden_util as gu
 KEYS = ["uout", "zout", "v_r_out", "F_H_out", "u_H_out"]
 # Strings with a large pluck amplitude and a large alpha amplify 1-ulp differences exponentially
 # in the reference scheme itself (see DESIGN.md "sensitivity"): looser bound on those fixtures.
-TOL = {"pluck_b24": 1e-6, "pluck_b2_long": 1e-4, "manufactured_b1": 1e-9}
+TOL = {"pluck_b24": 1e-6, "pluck_b2_long": 1e-4, "manufactured_b1": 1e-9, "manufactured_sr12k": 1e-9,
+       "manufactured_sr24k": 1e-9, "manufactured_sr48k": 1e-9, "manufactured_sr96k": 1e-9}
 
 
 @pytest.mark.parametrize("name", gu.golden_names())
@@ -32,6 +33,22 @@ def test_oracle_matches_reference_golden(oracle, name):
         assert gu.rel_l2(out["state_u"].numpy(), g["state_u_full"]) < tol
     # in-place u_H update (string.cpp:303)
     assert gu.rel_l2(inp["hammer_params"][2].numpy(), g["u_H_inplace"]) < tol
+
+
+def test_oracle_on_the_full_length_fixtures(oracle):
+    """Prefixes of the full-length fixtures of the BASELINE configs (the CUDA path is compared at full length on the GPU;
+    the dense-LU oracle is too slow for that here): bowed string 0.25 s of 4 s, 192 kHz hammer 60 of 9 598 steps (N_t = 237,
+    N_l = 581: an 820 x 820 LU per pass), and the calm first 10 ms of the chaotic nsynth-like string of configs[0]."""
+    for name, n, tol in (("allfixed_bow_b1_4s", 12000, 1e-9), ("finehammer192_b1", 62, 1e-10), ("pluck_b1_1s", 482, 1e-10)):
+        g = gu.load_golden(name)
+        inp = gu.build_inputs(g)
+        cut = lambda t: t[:, :n].contiguous() if (isinstance(t, __import__("torch").Tensor) and t.dim() >= 2 and t.size(1) == int(g["Nt"])) else t
+        inp = {k: ([cut(x) for x in v] if isinstance(v, list) and k.endswith("_params") else cut(v)) for k, v in inp.items()}
+        inp["Nt"] = n; inp["chunk_size"] = n
+        out = gu.run_process(oracle.forward_fn, inp)
+        for k in ("uout", "zout"):
+            err = gu.rel_l2(out[k].numpy(), g[k][:, :n - 2])
+            assert err < tol, (name, k, err)
 
 
 @pytest.mark.parametrize("name", ["pluck_b3", "hammer_b3", "bow_b3", "random_b6", "allfixed_pluck_b1"])
