@@ -165,8 +165,13 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
             sz = torch.zeros(B, Nt, p_host["Nx_l1"], **f64); sz[:, :2] = p["state_z"]
         else:
             su, sz = p["state_u"].clone(), p["state_z"].clone()
+        # hammer displacement: pre-loaded like the reference's Hammer module (simulator.py:573-578) and updated IN PLACE by the
+        # stepper (string.cpp:303) -- the reference saves the updated tensor as hammer_params.npz:u_H
+        uH = torch.zeros(B, Nt, **f64)
+        uH[:, :2] = -1e-3
+        uH[:, 1] += p_host["k"] * p["v_H"]
         args, res, keep_alive = build_args(
-            su, sz, kappa=p["kappa"], alpha=p["alpha"], pos=p["pos"], T60=p["T60"], phi_0=p["phi_0"], phi_1=p["phi_1"],
+            su, sz, u_H=uH, kappa=p["kappa"], alpha=p["alpha"], pos=p["pos"], T60=p["T60"], phi_0=p["phi_0"], phi_1=p["phi_1"],
             x_H=p["x_H"], w_H=p["w_H"], M_r=p["M_r"], alpha_H=p["alpha_H"], bow_mask=p["bow_mask"], hammer_mask=p["hammer_mask"],
             k=p_host["k"], theta_t=p_host["theta_t"], lambda_c=p_host["lambda_c"], relative_order=p_host["relative_order"],
             Nt=Nt, group_size=batch_size, synth=sampler.synth_dict(p), surface_integral=surface_integral,
@@ -194,9 +199,12 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
         row = pp["row_bytes"]
         pcm = {k: pp["pcm_" + k].index_select(0, idx)[:, :row].cpu().numpy() for k in ("u", "z", "w")}   # only kept audio crosses PCIe
         raw = {k: res[k].index_select(0, idx)[:, 2:].cpu().numpy() for k in ("uout", "zout", "v_r", "F_H", "u_H_out")}
-        sub = {k: (v.index_select(0, idx) if isinstance(v, torch.Tensor) and v.dim() > 0 and v.size(0) == B else v) for k, v in p.items()}
+        sub = dict(p)
+        for kx in sampler.SYNTH_KEYS:
+            sub[kx] = p[kx].index_select(0, idx)
         ctl = synth_controls(sampler.synth_dict(sub), len(kept), Nt, device)                  # the curves the stepper used
-        ctl_h = {k: ctl[k].cpu().numpy() for k in ("f0", "x_b", "v_b", "F_b", "u_H")}
+        ctl_h = {k: ctl[k].cpu().numpy() for k in ("f0", "x_b", "v_b", "F_b")}
+        ctl_h["u_H"] = uH.index_select(0, idx).cpu().numpy()
         f0 = ctl_h["f0"]
         sig0 = res["sig0"].cpu().numpy(); sig1 = res["sig1"].cpu().numpy()
         nt_, nl_ = sampler.derived_grid(torch.from_numpy(f0), p_host["kappa"][keep].view(-1, 1), p_host["k"], p_host["theta_t"],
@@ -242,7 +250,7 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
         for fut in pending:                     # the previous call's files must be on disk before a third call's arrays pile up
             fut.result()
         pending = new_jobs
-        del res, ctl, pp, su, sz, args, keep_alive
+        del res, ctl, pp, su, sz, uH, args, keep_alive
     for fut in pending:
         fut.result()
     pool.shutdown()
