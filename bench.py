@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--sweep", default="", help="comma-separated TOTAL string counts (BASELINE configs[4]: 1024,4096,16384,65536,"
                     "262144,1048576): each point is sharded over the ranks and run in waves of <= --strings per call, audio only")
     ap.add_argument("--no-drop-in", action="store_true", help="skip the reference-signature forward_fn leg")
+    ap.add_argument("--drop-in-batches", type=int, default=4, help="reference batches of the forward_fn leg (configs[1]: 100 // 24 = 4)")
     ap.add_argument("--async-steps", action="store_true", help="diagnostics: queue all timed steps without synchronising the host in "
                     "between (measured 10-15 %% slower per step on B200: launches queued behind a running call slow it down)")
     ap.add_argument("--p-a-max", type=float, default=None, help="override the pluck amplitude cap (diagnostics only)")
@@ -195,8 +196,8 @@ def algorithmic_work(p, counters, group, n_run):
 def run_sweep(a, points, rank, world, dev):
     """BASELINE configs[4]: batch sweep.  Every point = `total` nsynth-like strings in reference batches of GROUP, sharded
     over the ranks (whole batches, no collective), run in waves of <= a.strings strings per call with in-kernel control
-    synthesis and audio-only outputs.  Kernel time = CUDA events around every wave's call (plan creation and host sampling
-    excluded), max over ranks; wall time includes them."""
+    synthesis and audio-only outputs, parameters drawn on the GPU.  Kernel time = CUDA events around every wave's call, max
+    over ranks; wall time also includes parameter sampling and plan creation."""
     import torch
     import torch.distributed as dist
     from torch_fdtd_string_b200 import sampler
@@ -208,14 +209,18 @@ def run_sweep(a, points, rank, world, dev):
         mine = len(range(rank, groups, world)) * GROUP                 # round-robin over ranks (parallel.rank_batches)
         done, t_k, waves, nan = 0, 0.0, 0, 0
         out = None
+        n_waves = max(1, -(-mine // wave_cap))
+        per_wave = -(-(mine // GROUP) // n_waves) * GROUP              # equal waves (whole batches) instead of full + remainder
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         while done < mine:
-            n = min(wave_cap, mine - done)
-            ph = sampler.sample_nsynth_like(n, sr=SR, length=a.length, excitation=a.excitation, seed=50000 + 97 * rank + waves + total)
-            p = sampler.to_device(ph, dev)
+            n = min(per_wave, mine - done)
+            # parameters drawn on the GPU (sampler device=...): nothing but the plan's small read-back crosses PCIe
+            ph = sampler.sample_nsynth_like(n, sr=SR, length=a.length, excitation=a.excitation, seed=50000 + 97 * rank + waves + total,
+                                            device=dev)
+            p = ph
             Nt = ph["Nt"]
             if out is None or out["uout"].size(0) != n:
                 out = {k: torch.empty(n, Nt, dtype=torch.float64, device=dev) for k in ("uout", "zout")}
@@ -458,7 +463,7 @@ def main():
     drop_in = None
     if rank == 0 and not a.no_drop_in:
         try:
-            drop_in = run_drop_in(a, dev)
+            drop_in = run_drop_in(a, dev, a.drop_in_batches)
         except Exception as e:                                          # diagnostics leg: never takes the headline down
             drop_in = {"error": str(e)[:200]}
     if rank != 0:

@@ -1684,9 +1684,11 @@ int kernel_regs(void (*kern)(const KArgs)) {
 int env_int(const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; }
 double env_dbl(const char *name, double dflt) { const char *v = getenv(name); return v ? atof(v) : dflt; }
 
-// side streams (per device) so that the launches of different buckets overlap; shared by all plans of the device
+// side streams so that the launches of different buckets overlap.  Every plan owns its own set for its lifetime (calls of
+// different plans in flight on different caller streams must not serialise behind each other); released streams go back to
+// a per-device free list (work still queued on them stays ordered).
 std::mutex g_mu;
-std::map<int, std::vector<cudaStream_t>> g_side_streams;
+std::map<int, std::vector<cudaStream_t>> g_free_streams;
 std::map<int, bool> g_pool_ready;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "%s: %s", #x, cudaGetErrorString(e_)); rc = SFDTD_ERR_CUDA; goto done; } } while (0)
@@ -1768,6 +1770,7 @@ struct sfdtd_plan {
     size_t queue_words = 0, n_buckets = 0;
     cudaEvent_t fork = nullptr;
     std::vector<cudaEvent_t> joins;
+    std::vector<cudaStream_t> side;  // one per bucket (taken from / returned to the device's free list)
     bool verbose = false;
 };
 
@@ -1813,6 +1816,11 @@ extern "C" int sfdtd_plan_destroy(sfdtd_plan *plan, void *cuda_stream) {
     if (plan->block) cudaFreeAsync(plan->block, (cudaStream_t)cuda_stream);
     if (plan->fork) cudaEventDestroy(plan->fork);
     for (cudaEvent_t e : plan->joins) cudaEventDestroy(e);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        std::vector<cudaStream_t> &fl = g_free_streams[plan->dev];
+        fl.insert(fl.end(), plan->side.begin(), plan->side.end());
+    }
     if (prev != plan->dev && prev >= 0) cudaSetDevice(prev);
     delete plan;
     return SFDTD_OK;
@@ -2069,11 +2077,20 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
             cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             P->joins.push_back(e);
         }
-        std::lock_guard<std::mutex> lk(g_mu);
-        std::vector<cudaStream_t> &ss = g_side_streams[P->dev];
-        while (ss.size() < P->n_buckets) {
-            cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-            ss.push_back(st);
+        if (P->n_buckets > 1) {
+            std::lock_guard<std::mutex> lk(g_mu);
+            std::vector<cudaStream_t> &fl = g_free_streams[P->dev];
+            while (P->side.size() < P->n_buckets) {
+                // an IDLE released stream if there is one (a released stream may still run the call of its last plan: a new
+                // call queued behind it would serialise two independent calls), else a new one; beyond 256 streams reuse
+                cudaStream_t st = nullptr;
+                for (size_t q = 0; q < fl.size() && !st; q++)
+                    if (cudaStreamQuery(fl[q]) == cudaSuccess) { st = fl[q]; fl.erase(fl.begin() + q); }
+                cudaGetLastError();
+                if (!st && fl.size() >= 256) { st = fl.back(); fl.pop_back(); }
+                if (!st) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                P->side.push_back(st);
+            }
         }
     }
 done:
@@ -2108,8 +2125,7 @@ extern "C" int sfdtd_forward_plan(sfdtd_plan *P, const sfdtd_args *args, void *c
     K.Wtab = P->d_wtab; K.maxNl = P->d_maxNl; K.uH_carry = P->d_uH;
     if (P->queue_words) CK(cudaMemsetAsync(P->d_queue, 0, sizeof(int32_t) * P->queue_words, stream));
     const size_t nb = P->n_buckets;
-    std::lock_guard<std::mutex> lk(g_mu);          // side streams, kernel attributes
-    const std::vector<cudaStream_t> &ss = g_side_streams[P->dev];
+    const std::vector<cudaStream_t> &ss = P->side;
     if (nb > 1) CK(cudaEventRecord(P->fork, stream));
     for (size_t bi = 0; bi < nb; bi++) {
         const Launch &ln = P->launches[bi];
@@ -2167,9 +2183,14 @@ extern "C" int sfdtd_forward(const sfdtd_args *args, void *cuda_stream) {
     { const int v = validate(args); if (v != SFDTD_OK) return v; }
     if (args->Nt <= 2) return SFDTD_OK;
     sfdtd_plan *P = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = sfdtd_plan_create(args, cuda_stream, &P);
     if (rc != SFDTD_OK) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     rc = sfdtd_forward_plan(P, args, cuda_stream);
+    if (getenv("SFDTD_VERBOSE"))
+        fprintf(stderr, "[sfdtd] host: plan %.2f ms, launch %.2f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     char keep[sizeof g_err]; memcpy(keep, g_err, sizeof keep);
     sfdtd_plan_destroy(P, cuda_stream);               // stream-ordered: the scratch is released after the kernels
     memcpy(g_err, keep, sizeof keep);

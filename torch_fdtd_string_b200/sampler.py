@@ -55,41 +55,47 @@ def derived_grid(f0, kappa_rel, k, theta_t, lambda_c, alpha):
 
 
 def _u(lo, hi, n, gen):
-    return (hi - lo) * torch.rand(n, generator=gen, dtype=torch.float64) + lo
+    return (hi - lo) * torch.rand(n, generator=gen, dtype=torch.float64, device=gen.device) + lo
 
 
-def sample_nsynth_like(B, sr=48000, length=1.0, excitation="pluck", seed=1234, cfg=None):
-    """-> dict of compact CPU float64 tensors (+ python scalars)."""
+def sample_nsynth_like(B, sr=48000, length=1.0, excitation="pluck", seed=1234, cfg=None, device="cpu"):
+    """-> dict of compact float64 tensors (+ python scalars).  ``device``: where the draws are made and the tensors live
+    ("cpu": torch's CPU generator; a CUDA device: the GPU-side sampler -- same distributions, that device's generator, and
+    the min-f0 scan over the whole curve, which dominates on the host, runs on the GPU)."""
     c = dict(NSYNTH)
     if cfg:
         c.update(cfg)
-    g = torch.Generator().manual_seed(seed)
+    device = torch.device(device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    _rand = lambda n, **kw: torch.rand(n, generator=g, device=device, **kw)
+    _randn = lambda n, **kw: torch.randn(n, generator=g, device=device, **kw)
+    _ones = lambda: torch.ones(B, dtype=torch.bool, device=device)
     k = 1.0 / sr
     Nt = int(sr * length)
     theta_t = c["theta_t"] if c.get("theta_t") is not None else get_theta(c["kappa_max"], c["f0_min"], sr, c["lambda_c"])
     # masks (src/utils/misc.py:95-121)
     if excitation.endswith("bow"):
-        bow = torch.ones(B, dtype=torch.bool); ham = torch.zeros(B, dtype=torch.bool)
+        bow = _ones(); ham = ~_ones()
     elif excitation.endswith("hammer"):
-        bow = torch.zeros(B, dtype=torch.bool); ham = torch.ones(B, dtype=torch.bool)
+        bow = ~_ones(); ham = _ones()
     elif excitation.endswith("pluck"):
-        bow = torch.zeros(B, dtype=torch.bool); ham = torch.zeros(B, dtype=torch.bool)
+        bow = ~_ones(); ham = ~_ones()
     else:
-        bow = torch.rand(B, generator=g) > 0.5
-        ham = (torch.rand(B, generator=g) > 0.5) & ~bow
+        bow = _rand(B) > 0.5
+        ham = (_rand(B) > 0.5) & ~bow
     pluck = ~(bow | ham)
     kappa = _u(c["kappa_min"], c["kappa_max"], B, g)
     # f0 (simulator.py:210-234): constant or glissando, optional vibrato, then pre-correction
     f0_con = _u(c["f0_min"], c["f0_max"], B, g)
     f0_1 = _u(c["f0_min"], c["f0_max"], B, g)
     f0_2 = torch.minimum(torch.maximum(_u(c["f0_min"], c["f0_max"], B, g), f0_1 - c["f0_diff_max"]), f0_1 + c["f0_diff_max"])
-    tv = torch.randn(B, generator=g) >= 0.5
+    tv = _randn(B) >= 0.5
     f0_a = torch.where(tv, f0_1, f0_con); f0_b = torch.where(tv, f0_2, f0_con)
-    vib_off = torch.randn(B, generator=g) >= 0.5                      # True -> no vibrato
-    mod_frq = 5.0 * torch.rand(B, generator=g, dtype=torch.float64) + 3.0
-    mod_amp = c["f0_mod_max"] * torch.rand(B, generator=g, dtype=torch.float64)
-    vib_t0 = torch.floor((Nt // 2) * torch.rand(B, generator=g, dtype=torch.float64))
-    vib_sign = torch.sign(torch.randn(B, generator=g, dtype=torch.float64))
+    vib_off = _randn(B) >= 0.5                      # True -> no vibrato
+    mod_frq = 5.0 * _rand(B, dtype=torch.float64) + 3.0
+    mod_amp = c["f0_mod_max"] * _rand(B, dtype=torch.float64)
+    vib_t0 = torch.floor((Nt // 2) * _rand(B, dtype=torch.float64))
+    vib_sign = torch.sign(_randn(B, dtype=torch.float64))
     mod_amp = torch.where(vib_off, torch.zeros_like(mod_amp), mod_amp * vib_sign)
     Bc = (math.pi * kappa) ** 2                                        # Fletcher detune (fdm.py:143-158)
     w0 = (1 + (2 / math.pi) * Bc.sqrt() + 4 / math.pi ** 2 * Bc) * (1 + Bc).sqrt()
@@ -100,12 +106,12 @@ def sample_nsynth_like(B, sr=48000, length=1.0, excitation="pluck", seed=1234, c
     pos = _u(c["pos_min"], c["pos_max"], B, g)
     fmin, fmax = (1 / 240) * sr / 2, (1 / 4) * sr / 2
     T_f1 = _u(fmin + 1000, fmax, B, g)
-    T_f2 = fmin + (T_f1 - 1000 - fmin) * torch.rand(B, generator=g, dtype=torch.float64)
+    T_f2 = fmin + (T_f1 - 1000 - fmin) * _rand(B, dtype=torch.float64)
     T_t1 = _u(c["t60_min_1"], c["t60_max_1"], B, g)
     T_t2 = (T_t1 + _u(0, c["t60_diff_max"], B, g)).clamp(c["t60_min_2"], c["t60_max_2"])
     if c["sampling_T60"] == "fix":
-        T_f1 = torch.full((B,), 1000.0, dtype=torch.float64); T_f2 = torch.full((B,), 100.0, dtype=torch.float64)
-        T_t1 = torch.full((B,), 0.0 if c["lossless"] else float(c["t60_fixed"]), dtype=torch.float64); T_t2 = T_t1.clone()
+        T_f1 = torch.full((B,), 1000.0, dtype=torch.float64, device=device); T_f2 = torch.full((B,), 100.0, dtype=torch.float64, device=device)
+        T_t1 = torch.full((B,), 0.0 if c["lossless"] else float(c["t60_fixed"]), dtype=torch.float64, device=device); T_t2 = T_t1.clone()
     T60 = torch.stack([torch.stack([T_f1, T_t1], -1), torch.stack([T_f2, T_t2], -1)], 1)   # (B,2,2)
     # pluck shape (simulator.py:169-200; misc.py:60-72 triangular), rows n=0 and n=1 of state_u
     p_a = _u(c["p_a_min"], c["p_a_max"], B, g) * pluck
@@ -115,30 +121,30 @@ def sample_nsynth_like(B, sr=48000, length=1.0, excitation="pluck", seed=1234, c
     n_t, _ = derived_grid(f0_lo, kappa, k, theta_t, c["lambda_c"], alpha)
     N = Nx_t1
     n = (n_t + 1).view(-1, 1)
-    i = torch.arange(N, dtype=torch.float64).view(1, -1)
+    i = torch.arange(N, dtype=torch.float64, device=device).view(1, -1)
     vl = (p_a / p_x).view(-1, 1) / n
     vr = (p_a / (1 - p_x)).view(-1, 1) / n
     left = (vl * i).clamp(min=0)
     right = (vr * (i + 1) - vr * (N - n + 1)).clamp(min=0).flip(1)
     u0 = torch.minimum(left, right) * pluck.view(-1, 1)
     state_u = torch.stack([u0, u0], 1).contiguous()                    # v0 = 0 -> rows 0 and 1 equal
-    state_z = torch.zeros(B, 2, Nx_l1, dtype=torch.float64)
+    state_z = torch.zeros(B, 2, Nx_l1, dtype=torch.float64, device=device)
     # hammer (simulator.py:531-597)
     x_H = _u(c["x_H_min"], c["x_H_max"], B, g)
     v_H = _u(c["v_H_min"], c["v_H_max"], B, g)
     wgt = 1.0 - (v_H - c["v_H_min"]) / (c["v_H_max"] - c["v_H_min"])
-    M_r = (c["M_r_max"] - c["M_r_min"]) * torch.rand(B, generator=g, dtype=torch.float64) * wgt + c["M_r_min"]
+    M_r = (c["M_r_max"] - c["M_r_min"]) * _rand(B, dtype=torch.float64) * wgt + c["M_r_min"]
     w_H = _u(c["w_H_min"], c["w_H_max"], B, g)
-    alpha_H = torch.full((B,), c["alpha_H"], dtype=torch.float64)
+    alpha_H = torch.full((B,), c["alpha_H"], dtype=torch.float64, device=device)
     # bow (simulator.py:419-484)
     x_b1 = _u(c["x_b_min"], c["x_b_max"], B, g)
     x_b2 = (x_b1 + _u(-c["x_b_maxdiff"], c["x_b_maxdiff"], B, g)).clamp(c["x_b_min"], c["x_b_max"])
     v_b1 = _u(c["v_b_min"], c["v_b_max"], B, g); v_b2 = _u(c["v_b_min"], c["v_b_max"], B, g)
     F_b1 = _u(c["F_b_min"], c["F_b_max"], B, g)
     F_b2 = F_b1 + _u(-c["F_b_maxdiff"], c["F_b_maxdiff"], B, g).clamp(c["F_b_min"], c["F_b_max"])
-    pulloff = torch.where(torch.rand(B, generator=g) > 0.5,
-                          (3 * length / 4) * torch.rand(B, generator=g, dtype=torch.float64) + length / 4,
-                          torch.full((B,), -1.0, dtype=torch.float64))
+    pulloff = torch.where(_rand(B) > 0.5,
+                          (3 * length / 4) * _rand(B, dtype=torch.float64) + length / 4,
+                          torch.full((B,), -1.0, dtype=torch.float64, device=device))
     phi_0 = _u(c["phi_0_min"], c["phi_0_max"], B, g); phi_1 = _u(c["phi_1_min"], c["phi_1_max"], B, g)
     wid = _u(c["wid_min"], c["wid_max"], B, g)
     return dict(
@@ -163,7 +169,7 @@ def _f0_curve(p, Nt, k, t):
 def f0_min_over_time(p, Nt, k, block=4096):
     lo = None
     for s in range(0, Nt, block):
-        t = torch.arange(s + 1, min(s + block, Nt) + 1, dtype=torch.float64).view(1, -1)
+        t = torch.arange(s + 1, min(s + block, Nt) + 1, dtype=torch.float64, device=p["f0_a"].device).view(1, -1)
         m = _f0_curve(p, Nt, k, t).min(dim=1).values
         lo = m if lo is None else torch.minimum(lo, m)
     return lo
