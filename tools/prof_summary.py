@@ -74,6 +74,6 @@ with open(os.path.join(ROOT, "profiles", f"ncu_full_{tag}_bulk_kernel_hot_lines.
 json.dump(summary, open(os.path.join(ROOT, "profiles", f"ncu_full_{tag}_bulk_kernel_summary.json"), "w"), indent=1)
 json.dump({"kernel": d["Kernel Name"], "strings": strings, "steps": steps, "dram_bytes_read": summary["dram_bytes_read"],
            "dram_bytes_write": summary["dram_bytes_write"], "dram_bytes_per_string_step": summary["dram_bytes_per_string_step"],
-           "algorithmic_bytes_per_string_step": 88, "source": f"profiles/ncu_full_{tag}_bulk_kernel_summary.json"},
+           "algorithmic_bytes_per_string_step": int(sys.argv[5]) if len(sys.argv) > 5 else 40, "source": f"profiles/ncu_full_{tag}_bulk_kernel_summary.json"},
           open(os.path.join(ROOT, "profiles", f"ncu_traffic_{tag}.json"), "w"), indent=1)
 print(json.dumps(summary, indent=1))
