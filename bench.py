@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--async-steps", action="store_true", help="diagnostics: queue all timed steps without synchronising the host in "
                     "between (measured 10-15 %% slower per step on B200: launches queued behind a running call slow it down)")
     ap.add_argument("--p-a-max", type=float, default=None, help="override the pluck amplitude cap (diagnostics only)")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32 leg (the reference's `precision: single` preset on the fp32 kernels)")
+    ap.add_argument("--fp32-steps", type=int, default=2)
     return ap.parse_args()
 
 
@@ -247,6 +249,67 @@ def run_sweep(a, points, rank, world, dev):
     return rows
 
 
+def run_fp32(a, p, out64, dev, rank, world):
+    """The same workload on the fp32 kernels (SFDTD_F32: the reference's `precision: single`, its default preset): states,
+    solves and outputs float32, grid sizes from the reference's float32 get_derived_vars, per-step scalar tables in fp64.
+    Reported beside the fp64 headline with its own (FP32 FMA) roofline and its distance to the fp64 run of the same strings."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from torch_fdtd_string_b200 import sampler, _lib
+    from torch_fdtd_string_b200.forward_fn import Plan
+    B, Nt = p["B"], p["Nt"]
+    out = {n: torch.zeros(B, Nt, dtype=torch.float32, device=dev) for n in ("uout", "zout", "v_r", "F_H", "u_H_out")}
+    su = p["state_u"].float(); sz = p["state_z"].float()
+    su0, sz0 = su.clone(), sz.clone()
+    args, res, keep = sampler.compact_args(p, GROUP, skip_aux=a.skip_aux, counters=True, out=out, su=su, sz=sz, precision="single")
+    plan = Plan(args)
+
+    def one_step():
+        su.copy_(su0); sz.copy_(sz0); res["status"].zero_(); res["counters"].zero_()
+        plan.run(args)
+
+    one_step(); torch.cuda.synchronize()
+    counters = res["counters"].clone()
+    nan32 = torch.isnan(out["uout"][:, 2:]).any(dim=1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.fp32_steps):
+        one_step()
+        torch.cuda.synchronize()
+    e1.record(); torch.cuda.synchronize()
+    tt = torch.tensor([e0.elapsed_time(e1) * 1e-3 / a.fp32_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    per_step = float(tt)
+    plan.close()
+    flops, flops_exec, gpu_upd, _, _ = algorithmic_work(p, counters, GROUP, Nt)
+    peak = ctypes.c_double(0.0)
+    if _lib.load().sfdtd_measure_fma_peak(1, ctypes.byref(peak)) != 0 or peak.value <= 0:
+        peak.value = 74.4
+    # distance to the fp64 run of the same strings over the first 50 ms (later the chaotic strings of DESIGN "Sensitivity"
+    # decorrelate in any arithmetic), strings finite in both runs
+    n1 = min(Nt, 2 + int(0.05 * SR))
+    a64 = out64["uout"][:, 2:n1]; a32 = out["uout"][:, 2:n1].double()
+    ok = torch.isfinite(a64).all(dim=1) & torch.isfinite(a32).all(dim=1) & (a64.norm(dim=1) > 0)
+    err = ((a32[ok] - a64[ok]).norm(dim=1) / a64[ok].norm(dim=1))
+    q = torch.quantile(err, torch.tensor([0.5, 0.9, 0.99], dtype=torch.float64, device=dev)) if err.numel() else torch.zeros(3)
+    ss = world * B * (Nt - 2) / SR
+    return {"dtype": "f32", "value": ss / per_step, "unit": "string-seconds/s", "ms_per_step": per_step * 1e3, "steps": a.fp32_steps,
+            "grid_point_updates_per_s": world * gpu_upd / per_step,
+            "roofline": {"bound": "fp32_fma", "achieved": flops / per_step / 1e12, "peak": peak.value, "unit": "TFLOP/s",
+                         "frac": flops / per_step / 1e12 / peak.value, "frac_executed": flops_exec / per_step / 1e12 / peak.value,
+                         "peak_source": "measured (sfdtd_measure_fma_peak(1): register-resident FFMA chains, this GPU)"},
+            "nan_strings": int(nan32.sum()),
+            "mean_sweeps_per_step": float(counters[:, 1].sum()) / max(1.0, float(counters[:, 3].sum())),
+            "uout_rel_l2_vs_fp64_first_50ms_p50_p90_p99": [float(x) for x in q],
+            "note": "same strings and call as the fp64 headline on the fp32 kernels; the reference's own fp32-vs-fp64 distance on "
+                    "its 10 ms fixtures is 4e-5 ... 3e-4 (tests/golden/f32)"}
+
+
 def run_drop_in(a, dev, batches=4):
     """The literal drop-in: the reference's own call -- forward_fn(state_u (B,Nt,Nx), ...) with B = 24 fat tensors, one
     batch per call (src/task/simulate.py:65-76), `batches` calls = BASELINE configs[1] (num_samples=100 -> 4 batches) --
@@ -393,6 +456,16 @@ def main():
     bytes_ = B * (Nt - 2) * (n_ctl_reads + 5) * 8 + B * 2 * (p["Nx_t1"] + p["Nx_l1"]) * 8
     plan.close()
 
+    fp32 = None
+    if not a.no_fp32 and a.controls == "synth":
+        try:
+            fp32 = run_fp32(a, p, out, dev, rank, world)
+        except Exception as e:                                          # never takes the headline down
+            if world > 1:
+                raise
+            fp32 = {"error": str(e)[:300]}
+        torch.cuda.empty_cache()
+
     # ---- end to end through the public API with HOST buffers ----
     # every step: pinned host compact parameters -> H2D -> plan (prepass, one small D2H) -> stepper (controls synthesised in
     # the kernel) -> device post-processing (NaN / silence flags, l-infinity gain, PCM_24 quantisation: what the reference
@@ -525,7 +598,7 @@ def main():
         "grid_point_updates_per_s": world * gpu_upd / per_step,
         "mean_operator_widths": {"W_t": Wt_mean, "W_l": Wl_mean},
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e,
-        "drop_in": drop_in, "sweep": sweep,
+        "fp32": fp32, "drop_in": drop_in, "sweep": sweep,
         "gpu_launches": int(launches), "clocks": clk, "step_ms": [round(x, 2) for x in step_ms],
         "peak_device_memory_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
         "health": {"status_bits": status, "nan_strings": nan_strings,

@@ -34,7 +34,7 @@ extern "C" {
 #define SFDTD_ABI_VERSION 2
 
 /* dtype of all floating-point arrays */
-enum { SFDTD_F64 = 0 };
+enum { SFDTD_F64 = 0, SFDTD_F32 = 1 };
 
 /* flags */
 enum {
@@ -171,6 +171,11 @@ int sfdtd_synth_controls(const sfdtd_args *args, const sfdtd_array *f0, const sf
 int sfdtd_postprocess(const sfdtd_array *uout, const sfdtd_array *zout, int32_t B, int32_t n0, int32_t n_samples,
                       double silence_db, int32_t normalize, int32_t bits, int64_t pcm_pitch, uint8_t *is_nan,
                       uint8_t *is_silent, double *gain, void *pcm_u, void *pcm_z, void *pcm_w, void *cuda_stream);
+
+/* The same for float32 uout / zout (outputs of an SFDTD_F32 call); gain stays double. */
+int sfdtd_postprocess_f32(const sfdtd_array *uout, const sfdtd_array *zout, int32_t B, int32_t n0, int32_t n_samples,
+                          double silence_db, int32_t normalize, int32_t bits, int64_t pcm_pitch, uint8_t *is_nan,
+                          uint8_t *is_silent, double *gain, void *pcm_u, void *pcm_z, void *pcm_w, void *cuda_stream);
 
 /* Human-readable description of the last error on this thread. */
 const char *sfdtd_last_error(void);

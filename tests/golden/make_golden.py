@@ -50,6 +50,10 @@ CASES = dict(
     random_b24=dict(preset='nsynth', model='random', B=24, length=0.004, seed=3),
     pluck_b2_long=dict(preset='nsynth', model='pluck', B=2, length=0.1, seed=5),
     random_b4_long=dict(preset='nsynth', model='random', B=4, length=0.05, seed=9),
+    # strings below 52 Hz: more than 256 transverse rows (the 32-lane x 20-row kernels)
+    lowf0_pluck_b2=dict(preset='lowf0', model='pluck', B=2, length=0.004, seed=21, threads=4),
+    lowf0_hammer_b2=dict(preset='lowf0', model='hammer', B=2, length=0.004, seed=22, threads=4),
+    lowf0_bow_b2=dict(preset='lowf0', model='bow', B=2, length=0.004, seed=23, threads=4),
     # ---- full-length runs of the BASELINE configs (long format: audio outputs only, time-constant curves stored once) ----
     # configs[0]: single plucked string, nsynth-like, 1 s @ 48 kHz (reference ~8 min)
     pluck_b1_1s=dict(preset='nsynth', model='pluck', B=1, length=1.0, long=True, threads=1),
@@ -222,9 +226,36 @@ def merge_pert(name, win=480):
     print(f"{name}: merged perturbed-run sensitivity ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def run_single(name):
+    """The reference's `precision: single` arithmetic on the fixture's OWN inputs: the stored (double) inputs are rounded to
+    float32 and handed to the unmodified reference's process(); its outputs go into tests/golden/f32/<name>.npz.  They give
+    (a) the reference's own fp32-vs-fp64 distance on these strings and (b) the target of the fp32 kernels."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_util as gu
+    g = gu.load_golden(name)
+    inp = gu.build_inputs(g, dtype=torch.float32)
+    torch.set_num_threads(CASES.get(name, {}).get('threads', 2))
+    t0 = time.time()
+    with torch.no_grad():
+        res = sim.process(ref_driver.scratch_root(), inp["state_u"], inp["state_z"], inp["string_params"], inp["bow_params"],
+                          inp["hammer_params"], inp["bow_mask"], inp["hammer_mask"], inp["consts"], inp["Nt"],
+                          inp["chunk_size"], None, True, inp["relative_order"], inp["surface_integral"], inp["manufactured"])
+    uout, zout, state_u, state_z, v_r, F_H, u_H_o, sig0, sig1 = res
+    os.makedirs(os.path.join(HERE, "f32"), exist_ok=True)
+    path = os.path.join(HERE, "f32", f"{name}.npz")
+    np.savez_compressed(path, uout=uout.numpy(), zout=zout.numpy(), v_r_out=v_r.numpy(), F_H_out=F_H.numpy(),
+                        u_H_out=u_H_o.numpy(), state_u_last=state_u[:, -2:, :].numpy(), state_z_last=state_z[:, -2:, :].numpy())
+    d = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+    print(f"{name} (single): ref {time.time() - t0:.1f}s; fp32 vs fp64 reference: uout {d(uout.numpy(), g['uout']):.2e} "
+          f"zout {d(zout.numpy(), g['zout']):.2e} -> {os.path.getsize(path) / 1024:.0f} KiB", flush=True)
+
+
 if __name__ == "__main__":
     argv = sys.argv[1:]
-    if argv and argv[0] == "--merge-pert":
+    if argv and argv[0] == "--single":
+        for nm in argv[1:]:
+            run_single(nm)
+    elif argv and argv[0] == "--merge-pert":
         for nm in argv[1:]:
             merge_pert(nm, win=480 if CASES[nm].get('long') else 48)
     elif argv and argv[0] == "--perturbed":

@@ -241,11 +241,12 @@ def test_cuda_matches_oracle_on_seeded_groups(oracle, name, B):
     assert (cnt[:, 3] == Nt - 2).all()
 
 
-def test_single_precision_tensors_are_widened():
-    """The reference's `precision: single` preset hands float32 tensors to forward_fn: the drop-in computes in fp64 and
-    returns float32 (same dtype as the reference would), equal to the fp64 run up to float32 rounding; the in-place
-    state / u_H updates land in the caller's float32 tensors."""
+def test_single_precision_tensors_are_widened(monkeypatch):
+    """SFDTD_WIDEN_F32=1: float32 tensors (the reference's `precision: single` preset) are computed in fp64 and returned
+    as float32 (same dtype as the reference would), equal to the fp64 run up to float32 rounding; the in-place state /
+    u_H updates land in the caller's float32 tensors.  (Default: the fp32 kernels, tests/test_gpu_fp32.py.)"""
     from torch_fdtd_string_b200 import forward_fn
+    monkeypatch.setenv("SFDTD_WIDEN_F32", "1")
     g = gu.load_golden("random_b6")
     i64 = gu.build_inputs(g, device="cuda")
     i32 = gu.build_inputs(g, dtype=torch.float32, device="cuda")

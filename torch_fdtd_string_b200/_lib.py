@@ -7,13 +7,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SFDTD_LIB") or os.path.join(HERE, "libsfdtd.so")     # SFDTD_LIB: A/B builds of the same ABI
 
 SFDTD_ABI_VERSION = 2
-SFDTD_F64 = 0
+SFDTD_F64, SFDTD_F32 = 0, 1
 SURFACE_INTEGRAL, MANUFACTURED, SAVE_STATE, SKIP_AUX = 1, 2, 4, 8
 ST_SOLVER_CAP, ST_OUTER_CAP, ST_HAMMER_CAP, ST_BOW_WINDOW, ST_RANGE = 1, 2, 4, 8, 16
 
 EXPORTS = ["sfdtd_forward", "sfdtd_last_error", "sfdtd_abi_version", "sfdtd_launch_count",
            "sfdtd_measure_fma_peak", "sfdtd_plan_create", "sfdtd_forward_plan", "sfdtd_plan_destroy",
-           "sfdtd_synth_controls", "sfdtd_postprocess"]
+           "sfdtd_synth_controls", "sfdtd_postprocess", "sfdtd_postprocess_f32"]
 
 
 class Array(ctypes.Structure):
@@ -80,6 +80,8 @@ def load():
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         lib.sfdtd_postprocess.restype = ctypes.c_int
+        lib.sfdtd_postprocess_f32.argtypes = lib.sfdtd_postprocess.argtypes
+        lib.sfdtd_postprocess_f32.restype = ctypes.c_int
         if lib.sfdtd_abi_version() != SFDTD_ABI_VERSION:
             raise RuntimeError("libsfdtd.so ABI version mismatch")
         _lib = lib

@@ -70,7 +70,6 @@ constexpr int NI = 8;               // ints per time step
 constexpr int NOUT = 5;             // staged outputs per step
 constexpr int NCONST = 8;           // per-string constants kept in shared memory
 constexpr int GS_CAP = 60;          // cap on block Gauss-Seidel sweeps per solve
-constexpr float GS_TOL = 1e-13f;    // predicted relative max-norm error of the transverse block that ends the sweeps
 constexpr int NLA_I = 5;            // longitudinal arrays per string, independent mode: Z1 Z2 ZA ZB RL
 constexpr int NLA_G = 6;            // grouped mode: + ZP (previous fixed-point iterate)
 // time steps per scalar-table block.  Independent mode: 16 = one step per lane of a 16-lane string, so that the table code
@@ -80,6 +79,13 @@ constexpr int TBS_I = 16, TBS_G = 8;
 constexpr int TBS_MAX = TBS_I > TBS_G ? TBS_I : TBS_G;
 #ifndef SFDTD_PREDICT_SWEEPS
 #define SFDTD_PREDICT_SWEEPS 1
+#endif
+// fewest sweeps of a step's first solve: with / without a longitudinal right-hand side of its own (keep_l > 0)
+#ifndef SFDTD_MIN_SW_L
+#define SFDTD_MIN_SW_L 4
+#endif
+#ifndef SFDTD_MIN_SW
+#define SFDTD_MIN_SW 3
 #endif
 #ifndef SFDTD_DEFAULT_WLMIN
 #define SFDTD_DEFAULT_WLMIN 16      // smallest longitudinal allocation class (rows incl. guards)
@@ -118,6 +124,7 @@ struct KArgs {
     sfdtd_args a;
     sfdtd_synth sy;                 // copy of *a.synth (valid when has_synth)
     int32_t has_synth;
+    int32_t f32;                    // SFDTD_F32 call: grid sizes from the reference's float32 evaluation of get_derived_vars
     double k, ik, k2, k4, th, omth, tt1, tt2, lamc, order, mhd;
     const int32_t *Wtab;            // [n_groups][Nt]  W_t | W_l << 16  (batch-max operator widths, misc.cpp:119-127)
     const int32_t *ids;             // independent mode: string ids
@@ -185,8 +192,8 @@ __device__ __forceinline__ double ctl_vb(const KArgs &A, int b, int n) { return 
 __device__ __forceinline__ double ctl_Fb(const KArgs &A, int b, int n) { return A.has_synth ? sy_Fb(A.sy, b, n + A.sy.t_0) : ldx(A.a.F_b, b, n); }
 __device__ __forceinline__ double ctl_wid(const KArgs &A, int b, int n) { return A.has_synth ? A.sy.wid[b] : ldx(A.a.wid, b, n); }
 // pre-loaded content of hammer_params[2] at sample n (string.cpp:303 adds the new displacement onto it)
-__device__ __forceinline__ double ctl_uH(const KArgs &A, int b, int n) {
-    if (A.a.u_H.ptr) return ldx(A.a.u_H, b, n);
+template <typename T> __device__ __forceinline__ double ctl_uH(const KArgs &A, int b, int n) {
+    if (A.a.u_H.ptr) return (double)((const T *)A.a.u_H.ptr)[(int64_t)b * A.a.u_H.bs + (int64_t)n * A.a.u_H.ts];
     return A.has_synth ? sy_uH(A.sy, b, n + A.sy.t_0) : 0.0;
 }
 
@@ -204,7 +211,29 @@ __device__ __forceinline__ double frcp(double x) {
 // ---- get_derived_vars (string.cpp:16-41), reference operation order, no FMA contraction ----------
 // floor(1/h) decides the grid sizes: one ulp flips them, so this part is evaluated exactly like the reference.
 struct Derived { double gamma, K, Nt, ht, Nl, hl; };
+// the same in float32, as the reference's `precision: single` run evaluates it (tensors float32, C++ scalars rounded to
+// float32 by ATen): its floor(1/h) can differ from the double one, and the grid size decides the whole waveform
+__device__ __forceinline__ Derived derive_f32(float f0, float kappa_rel, float alpha, const KArgs &A) {
+    Derived d;
+    const float pi = (float)M_PI, k = (float)A.k, k2 = (float)A.k2, k4 = (float)A.k4;
+    const float gamma = __fmul_rn(2.0f, f0);
+    const float kappa = __fmul_rn(gamma, kappa_rel);
+    const float t0 = __fdiv_rn(__fmul_rn(pi, kappa), gamma);
+    const float IHP = __fmul_rn(t0, t0);
+    const float K = __fmul_rn(__fsqrt_rn(IHP), __fdiv_rn(gamma, pi));
+    const float g2 = __fmul_rn(gamma, gamma), g4 = __fmul_rn(g2, g2), K2 = __fmul_rn(K, K);
+    const float in = __fadd_rn(__fmul_rn(g4, k4), __fmul_rn(__fmul_rn(__fmul_rn(16.0f, K2), k2), (float)A.tt1));
+    const float num = __fadd_rn(__fmul_rn(g2, k2), __fsqrt_rn(in));
+    const float h1 = __fmul_rn((float)A.lamc, __fsqrt_rn(__fdiv_rn(num, (float)A.tt2)));
+    const float Nt = floorf(__frcp_rn(h1));
+    const float h2 = __fmul_rn(__fmul_rn(__fmul_rn((float)A.lamc, gamma), alpha), k);
+    const float Nl = floorf(__frcp_rn(h2));
+    d.Nt = (double)Nt; d.ht = (double)__frcp_rn(Nt); d.Nl = (double)Nl; d.hl = (double)__frcp_rn(Nl);
+    d.gamma = (double)gamma; d.K = (double)K;
+    return d;
+}
 __device__ __forceinline__ Derived derive(double f0, double kappa_rel, double alpha, const KArgs &A) {
+    if (A.f32) return derive_f32((float)f0, (float)kappa_rel, (float)alpha, A);
     Derived d;
     const double gamma = __dmul_rn(2.0, f0);
     const double kappa = __dmul_rn(gamma, kappa_rel);
@@ -231,14 +260,15 @@ __device__ __forceinline__ int clampN(double v) { return (int)fmin(fmax(v, 0.0),
 // Also a per-string estimate of the nonlinearity  phi/h^2 Lambda^2  of the first step (from state row n-1): it predicts
 // how many block sweeps the string needs, and the host sorts the strings of a launch by it so that the strings
 // sharing a warp converge in about the same number of sweeps.
+template <typename T>
 __global__ void sfdtd_prepass_kernel(const __grid_constant__ KArgs A, int32_t *maxNt, int32_t *maxNl, float *est) {
     const int b = blockIdx.x;
     const int Nt = A.a.Nt;
     double fm = INFINITY;
     double dm = 0.0;
     {
-        const double *su1 = (const double *)A.a.state_u.ptr + (int64_t)b * A.a.state_u.bs + A.a.state_u.ts;
-        for (int i = 1 + threadIdx.x; i < A.a.Nx_t1; i += blockDim.x) dm = fmax(dm, fabs(su1[i] - su1[i - 1]));
+        const T *su1 = (const T *)A.a.state_u.ptr + (int64_t)b * A.a.state_u.bs + A.a.state_u.ts;
+        for (int i = 1 + threadIdx.x; i < A.a.Nx_t1; i += blockDim.x) dm = fmax(dm, fabs((double)su1[i] - (double)su1[i - 1]));
         for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(FULLMASK, dm, o));
     }
     __shared__ double sd[32];
@@ -282,10 +312,10 @@ __global__ void sfdtd_width_kernel(const __grid_constant__ KArgs A, int32_t *Wta
 }
 
 // ---- warp helpers over the L lanes of one string -------------------------------------------------
-template <int L> __device__ __forceinline__ double shup(double v, int d) { return __shfl_up_sync(FULLMASK, v, d, L); }
-template <int L> __device__ __forceinline__ double shdn(double v, int d) { return __shfl_down_sync(FULLMASK, v, d, L); }
-template <int L> __device__ __forceinline__ double shix(double v, int s) { return __shfl_sync(FULLMASK, v, s, L); }
-template <int L> __device__ __forceinline__ double red_sum(double v) {
+template <int L, typename T> __device__ __forceinline__ T shup(T v, int d) { return __shfl_up_sync(FULLMASK, v, d, L); }
+template <int L, typename T> __device__ __forceinline__ T shdn(T v, int d) { return __shfl_down_sync(FULLMASK, v, d, L); }
+template <int L, typename T> __device__ __forceinline__ T shix(T v, int s) { return __shfl_sync(FULLMASK, v, s, L); }
+template <int L, typename T> __device__ __forceinline__ T red_sum(T v) {
 #pragma unroll
     for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o, L);
     return v;
@@ -365,7 +395,11 @@ template <int L> constexpr int ilog2() { return L <= 1 ? 0 : 1 + ilog2<L / 2>();
 
 // |x| as the high word of the double: monotone in |x| for integer compares; NaN and inf sort above every finite value
 __device__ __forceinline__ unsigned hi_abs(double v) { return (unsigned)__double2hiint(v) & 0x7fffffffu; }
-__device__ __forceinline__ float hi_to_float(unsigned h) { return (float)__hiloint2double((int)h, 0); }   // > FLT_MAX -> inf, NaN -> NaN
+__device__ __forceinline__ unsigned hi_abs(float v) { return __float_as_uint(v) & 0x7fffffffu; }          // fp32 build: the whole word
+template <typename T> __device__ __forceinline__ float hi_to_float(unsigned h) {
+    if (sizeof(T) == 8) return (float)__hiloint2double((int)h, 0);                                        // > FLT_MAX -> inf, NaN -> NaN
+    return __uint_as_float(h);
+}
 template <int L> __device__ __forceinline__ unsigned red_maxu(unsigned v) {
 #pragma unroll
     for (int o = L / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULLMASK, v, o, L));
@@ -376,19 +410,49 @@ __device__ __forceinline__ double nan0(double v) {   // nan_to_num (string.cpp:2
     if (isinf(v)) return v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
     return v;
 }
+__device__ __forceinline__ float nan0(float v) {
+    if (v != v) return 0.0f;
+    if (isinf(v)) return v > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+    return v;
+}
+// arithmetic type of a stepper build: double (SFDTD_F64, the parity mode) or float (SFDTD_F32, the reference's `precision:
+// single`).  State rows, the per-step working set, the linear solves and the audio outputs are of that type; the per-step
+// scalar table, the bow window, the hammer contact loop and the control curves are evaluated in double in both builds.
+template <typename T> struct Real;
+template <> struct Real<double> {
+    static constexpr float GS_TOL = 1e-13f;          // predicted relative max-norm error of the transverse block that ends the sweeps
+    static constexpr float E_FLOOR = 0.f;            // a relative change at or below this is round-off: converged
+    static constexpr float RATE_MIN = 0.f;           // the contraction rate is only measured from changes above this
+};
+template <> struct Real<float> {
+    // float32 round-off of one solve is ~2e-7 of the solution's max-norm: the sweeps run down to it (the reference's direct
+    // float32 solve is that accurate, and per-step errors accumulate linearly over the run)
+    static constexpr float GS_TOL = 1e-7f;
+    static constexpr float E_FLOOR = 4e-7f;
+    static constexpr float RATE_MIN = 2e-5f;
+};
+__device__ __forceinline__ float frcp(float x) {     // MUFU.RCP + one Newton step
+    const float r = __fdividef(1.0f, x);
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { typedef double2 type; };
+template <> struct Vec2<float> { typedef float2 type; };
+__device__ __forceinline__ double t_cospi(double x) { return cospi(x); }
+__device__ __forceinline__ float t_cospi(float x) { return cospif(x); }
 
 // ---- partitioned Thomas: local LU of the ET-1 interior rows + PCR over the L interface rows -------
-template <int L, int ET> struct TriSolver {
+template <typename T, int L, int ET> struct TriSolver {
     static constexpr int M = ET - 1;
     static constexpr int LV = ilog2<L>();
-    double inv[M], lw[M], cp[M], V[M], W[M];
-    double ae, ce, k1[LV], k2[LV], invB;
+    T inv[M], lw[M], cp[M], V[M], W[M];
+    T ae, ce, k1[LV], k2[LV], invB;
 
-    __device__ __forceinline__ void factor(const double (&a)[ET], const double (&b)[ET], const double (&c)[ET], int ln) {
-        double cprev = 0.0;
+    __device__ __forceinline__ void factor(const T (&a)[ET], const T (&b)[ET], const T (&c)[ET], int ln) {
+        T cprev = T(0);
 #pragma unroll
         for (int r = 0; r < M; r++) {
-            const double den = fma(-a[r], cprev, b[r]);
+            const T den = fma(-a[r], cprev, b[r]);
             inv[r] = frcp(den);
             cp[r] = c[r] * inv[r];
             lw[r] = a[r] * inv[r];
@@ -402,48 +466,48 @@ template <int L, int ET> struct TriSolver {
 #pragma unroll
         for (int r = M - 2; r >= 0; r--) { V[r] = fma(-cp[r], V[r + 1], V[r]); W[r] = -cp[r] * W[r + 1]; }
         ae = a[ET - 1]; ce = c[ET - 1];
-        const double Vn0 = shdn<L>(V[0], 1), Wn0 = shdn<L>(W[0], 1);
-        double Ar = -ae * V[M - 1];
-        double Br = b[ET - 1] - ae * W[M - 1] - ce * Vn0;
-        double Cr = -ce * Wn0;
-        if (ln == 0) Ar = 0.0;
-        if (ln == L - 1) { Cr = 0.0; Br = b[ET - 1] - ae * W[M - 1]; }
+        const T Vn0 = shdn<L>(V[0], 1), Wn0 = shdn<L>(W[0], 1);
+        T Ar = -ae * V[M - 1];
+        T Br = b[ET - 1] - ae * W[M - 1] - ce * Vn0;
+        T Cr = -ce * Wn0;
+        if (ln == 0) Ar = T(0);
+        if (ln == L - 1) { Cr = T(0); Br = b[ET - 1] - ae * W[M - 1]; }
 #pragma unroll
         for (int lv = 0; lv < LV; lv++) {
             const int s = 1 << lv;
-            const double iB = frcp(Br);
-            const double iBm = shup<L>(iB, s), iBp = shdn<L>(iB, s);
-            const double Am = shup<L>(Ar, s), Cm = shup<L>(Cr, s);
-            const double Ap = shdn<L>(Ar, s), Cp = shdn<L>(Cr, s);
+            const T iB = frcp(Br);
+            const T iBm = shup<L>(iB, s), iBp = shdn<L>(iB, s);
+            const T Am = shup<L>(Ar, s), Cm = shup<L>(Cr, s);
+            const T Ap = shdn<L>(Ar, s), Cp = shdn<L>(Cr, s);
             const bool hm = ln >= s, hp = ln + s < L;
-            const double q1 = hm ? Ar * iBm : 0.0, q2 = hp ? Cr * iBp : 0.0;
+            const T q1 = hm ? Ar * iBm : T(0), q2 = hp ? Cr * iBp : T(0);
             k1[lv] = q1; k2[lv] = q2;
-            Br = Br - (hm ? Cm * q1 : 0.0) - (hp ? Ap * q2 : 0.0);
-            Ar = hm ? -Am * q1 : 0.0;
-            Cr = hp ? -Cp * q2 : 0.0;
+            Br = Br - (hm ? Cm * q1 : T(0)) - (hp ? Ap * q2 : T(0));
+            Ar = hm ? -Am * q1 : T(0);
+            Cr = hp ? -Cp * q2 : T(0);
         }
         invB = frcp(Br);
     }
 
     // d: right-hand side in, solution out
-    __device__ __forceinline__ void solve(double (&d)[ET], int ln) const {
-        double Y[M];
+    __device__ __forceinline__ void solve(T (&d)[ET], int ln) const {
+        T Y[M];
         Y[0] = d[0] * inv[0];
 #pragma unroll
         for (int r = 1; r < M; r++) Y[r] = fma(-lw[r], Y[r - 1], d[r] * inv[r]);
 #pragma unroll
         for (int r = M - 2; r >= 0; r--) Y[r] = fma(-cp[r], Y[r + 1], Y[r]);
-        double Yn0 = shdn<L>(Y[0], 1);
+        T Yn0 = shdn<L>(Y[0], 1);
         // (no boundary select: ce = 0 in the last lane, whose last row has no right neighbour; the shuffle returns its own Y[0])
-        double D = d[ET - 1] - ae * Y[M - 1] - ce * Yn0;
+        T D = d[ET - 1] - ae * Y[M - 1] - ce * Yn0;
 #pragma unroll
         for (int lv = 0; lv < LV; lv++) {
             const int s = 1 << lv;
-            const double Dm = shup<L>(D, s), Dp = shdn<L>(D, s);
+            const T Dm = shup<L>(D, s), Dp = shdn<L>(D, s);
             D = D - k1[lv] * Dm - k2[lv] * Dp;     // k1/k2 are 0 where the neighbour does not exist
         }
-        const double xe = D * invB;
-        double p = shup<L>(xe, 1);
+        const T xe = D * invB;
+        T p = shup<L>(xe, 1);
         // (no boundary select: the left spike V is 0 in lane 0, whose first row has no left neighbour)
 #pragma unroll
         for (int r = 0; r < M; r++) d[r] = Y[r] - V[r] * p - W[r] * xe;
@@ -481,18 +545,18 @@ __device__ __forceinline__ void interp_row(float s, int o, int in_last, int &i0,
 }
 
 // gather through a packed pair of BYTE offsets (lo 16 bits | hi 16 bits): one add per address instead of unpack + scale + add
-__device__ __forceinline__ double ldb(const double *base, int byte_off) { return *(const double *)((const char *)base + byte_off); }
+template <typename T> __device__ __forceinline__ T ldb(const T *base, int byte_off) { return *(const T *)((const char *)base + byte_off); }
 
 // select element `slot` of a register array without dynamic indexing
-template <int ET> __device__ __forceinline__ double pick(const double (&v)[ET], int slot) {
-    double o = 0.0;
+template <int ET, typename T> __device__ __forceinline__ T pick(const T (&v)[ET], int slot) {
+    T o = T(0);
 #pragma unroll
     for (int r = 0; r < ET; r++) o = (r == slot) ? v[r] : o;
     return o;
 }
-template <int L, int ET> __device__ __forceinline__ double fetch_row(const double (&v)[ET], int idx) {
+template <int L, int ET, typename T> __device__ __forceinline__ T fetch_row(const T (&v)[ET], int idx) {
     idx = idx < 0 ? 0 : (idx > L * ET - 1 ? L * ET - 1 : idx);
-    const double mine = pick<ET>(v, idx % ET);
+    const T mine = pick<ET>(v, idx % ET);
     return shix<L>(mine, idx / ET);
 }
 
@@ -508,14 +572,16 @@ __host__ __device__ inline int slot_spacing(int n, int L) {
     else if ((n & 15) == 0) n += 2;   // one string per half-warp: the slots only should not start in the same bank
     return n;
 }
-__host__ __device__ inline int slot_fixed_doubles(int L, int ET, bool grouped) {
+// (tsz: sizeof of the build's arithmetic type; the row arrays and the longitudinal arrays are of that type)
+__host__ __device__ inline int slot_fixed_doubles(int L, int ET, bool grouped, int tsz) {
     const int LE = L * ET;
     const int TBS = grouped ? TBS_G : TBS_I;
-    const int n = TBS * (grouped ? NV_G : NV_I) + TBS * NI / 2 + TBS * NOUT + NCONST + (LE + L + 2) + 2 * (LE + L + 6) + (grouped ? LE + L : 0);
+    const int rows = (LE + L + 2) + 2 * (LE + L + 6) + (grouped ? LE + L : 0);
+    const int n = TBS * (grouped ? NV_G : NV_I) + TBS * NI / 2 + TBS * NOUT + NCONST + (rows * tsz + 7) / 8;
     return slot_spacing(n, L);
 }
-__host__ __device__ inline int slot_long_doubles(int W, bool grouped, int L) {
-    const int n = ((grouped ? NLA_G : NLA_I) * W + 2 * W + (W + 1) / 2 + 1) & ~1;
+__host__ __device__ inline int slot_long_doubles(int W, bool grouped, int L, int tsz) {
+    const int n = ((((grouped ? NLA_G : NLA_I) * W + 2 * W) * tsz + 7) / 8 + (W + 1) / 2 + 1) & ~1;
     return L <= 8 ? slot_spacing(n, L) : n;
 }
 __host__ __device__ inline int long_rows(int maxNl) { return (maxNl + 1 + WL_MARGIN + 2 + 1) & ~1; }   // + 2 guards, even
@@ -548,7 +614,7 @@ struct TabIn {
     bool bowm, hamm;
     const int32_t *Wrow;
 };
-template <bool GROUPED>
+template <typename T, bool GROUPED>
 __device__ __forceinline__ void fill_table_row_impl(const KArgs &A, const TabIn &in, int n, double *t, int *ti) {
     const sfdtd_args &a = A.a;
     const int b = in.b;
@@ -622,24 +688,26 @@ __device__ __forceinline__ void fill_table_row_impl(const KArgs &A, const TabIn 
     if (GROUPED) { t[T_TOLT] = pow(d.ht, A.order); t[T_TOLL] = pow(d.hl, A.order); t[T_FB] = ctl_Fb(A, b, n); }
     t[T_CTR] = ctr; t[T_WID] = wid;
     t[T_VB] = ctl_vb(A, b, n);
-    t[T_UHPRE] = ctl_uH(A, b, n);
+    t[T_UHPRE] = ctl_uH<T>(A, b, n);
     t[T_S0K] = s0k; t[T_S1K] = s1k; t[T_GA2] = g * alpha2;
     ti[I_NT] = N_t; ti[I_NL] = N_l; ti[I_R] = R | (oob << 30); ti[I_WLS] = WLs;
     ti[I_RK] = min(R, keep_flat); ti[I_KEEPL] = keep_flat - in.NXT;
     ti[I_IDXH] = (int)fmin(fmax(floor(__dmul_rn(xH, (double)(N_t - 1))), 0.0), (double)(in.LE - 1));
     ti[I_IC] = ic;
 }
-template <bool GROUPED>
+template <typename T, bool GROUPED>
 __device__ __noinline__ void fill_table_row(const KArgs &A, const TabIn &in, int n, double *t, int *ti) {
-    fill_table_row_impl<GROUPED>(A, in, n, t, ti);
+    fill_table_row_impl<T, GROUPED>(A, in, n, t, ti);
 }
 #ifndef SFDTD_TAB_INLINE_I
 #define SFDTD_TAB_INLINE_I 1        // 1: the independent-mode kernels inline the table code (measured: the call costs them 4 %)
 #endif
 
 // ======================================================================================================
-template <int L, int ET, bool GROUPED, bool MANUF>
+template <typename T, int L, int ET, bool GROUPED, bool MANUF>
 __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
+    constexpr int TSZ = (int)sizeof(T);
+    constexpr float GS_TOL = Real<T>::GS_TOL;
     constexpr int TB = GROUPED ? TBS_G : TBS_I;
     constexpr int LE = L * ET;
     constexpr int NLA = GROUPED ? NLA_G : NLA_I;
@@ -648,7 +716,8 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
     constexpr int O_TABI = TB * NV, O_OST = O_TABI + TB * NI / 2, O_CST = O_OST + TB * NOUT, O_QS = O_CST + NCONST;
     // row arrays (qs, UA, UB, RC) are indexed through PR(): one pad double per ET rows, so that the blocked accesses
     // "lane l touches rows l*ET + c" fall into distinct banks (stride ET+1 doubles instead of ET)
-    constexpr int O_UA = O_QS + (LE + L + 2) + 4, O_UB = O_UA + (LE + L + 6), O_RC = O_UB + (LE + L + 2);
+    // (offsets of the row arrays in elements of T from the start of the row region SR = (T *)(S + O_QS))
+    constexpr int O_UA = (LE + L + 2) + 4, O_UB = O_UA + (LE + L + 6), O_RC = O_UB + (LE + L + 2);
     auto PR = [](int i) { return i + (i + ET) / ET - 1; };            // i >= -ET
     extern __shared__ __align__(16) double smem[];
     const sfdtd_args &a = A.a;
@@ -682,32 +751,34 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
     constexpr int O_BOARD = GROUPED ? GB_DOUBLES : 0;
     float *xaxs = (float *)(smem + O_BOARD);                          // [NXT] (only when the bow axis is needed)
     const int xoff = O_BOARD + (A.need_xax ? (((NXT + 3) / 4) * 2) : 0);
-    double *const S = smem + xoff + (size_t)sl * slot_fixed_doubles(L, ET, GROUPED);
-    double *Lb = smem + xoff + (size_t)nslots * slot_fixed_doubles(L, ET, GROUPED);
+    double *const S = smem + xoff + (size_t)sl * slot_fixed_doubles(L, ET, GROUPED, TSZ);
+    double *Lbd = smem + xoff + (size_t)nslots * slot_fixed_doubles(L, ET, GROUPED, TSZ);
     int WLp;
     if (GROUPED) {
         // per-string longitudinal allocation (sized by the string's own largest N_l), offsets by a prefix sum
-        int *ioffs = (int *)Lb;                                       // [nslots + 2]
+        int *ioffs = (int *)Lbd;                                      // [nslots + 2]
         WLp = long_rows(A.maxNl[b]);
-        if (ln == 0) ioffs[sl + 1] = slot_long_doubles(WLp, true, L);
+        if (ln == 0) ioffs[sl + 1] = slot_long_doubles(WLp, true, L, TSZ);
         __syncthreads();
         if (tid == 0) { ioffs[0] = ((nslots + 2) / 2 + 1) & ~1; for (int q = 0; q < nslots; q++) ioffs[q + 1] += ioffs[q]; }
         __syncthreads();
         const int off = ioffs[sl];
         __syncthreads();
-        Lb += off;
+        Lbd += off;
     } else {
         WLp = A.WLp;
-        Lb += (size_t)sl * slot_long_doubles(WLp, false, L);
+        Lbd += (size_t)sl * slot_long_doubles(WLp, false, L, TSZ);
     }
+    T *const Lb = (T *)Lbd;
     const int WLa = WLp - 2;                                          // usable longitudinal rows (guards at -1 and WLa)
     double *const tab = S;                                            // [TB][NV]
     int *const tabi = (int *)(S + O_TABI);                            // [TB][NI]
     double *const ost = S + O_OST;                                    // [TB][NOUT]
     double *const cst = S + O_CST;                                    // [NCONST]
-    double *const qs = S + O_QS;                                      // [LE + L + 2], PR()-indexed
-    double *const RC = S + O_RC;                                      // [LE + L] bow weights (grouped mode only), PR()-indexed
-    double *const LW = Lb + NLA * WLp;                                // [WLp][2] Int_lt weights
+    T *const SR = (T *)(S + O_QS);                                    // row region: qs | UA | UB | RC
+    T *const qs = SR;                                                 // [LE + L + 2], PR()-indexed
+    T *const RC = SR + O_RC;                                          // [LE + L] bow weights (grouped mode only), PR()-indexed
+    T *const LW = Lb + NLA * WLp;                                     // [WLp][2] Int_lt weights
     int *const LI = (int *)(LW + 2 * WLp);                            // [WLp]    Int_lt indices i0 | i1 << 16
     // transverse state rows n-1 / n-2 (in S, guards: 2 each side) and longitudinal arrays (in Lb, guard at [-1]); offsets swap
     int u1o = O_UA, u2o = O_UB;
@@ -791,29 +862,29 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
 
     // ---- initial state: rows n-2, n-1 ----
     {
-        for (int j = ln; j < 2 + 2 * (LE + L + 6) + (GROUPED ? LE + L : 0); j += L) S[O_QS + LE + L + j] = 0.0;      // UA, UB (with guards), RC
-        for (int j = ln; j < NLA * WLp; j += L) Lb[j] = 0.0;
-        for (int j = ln; j < WLp; j += L) { LW[2 * j] = 0.0; LW[2 * j + 1] = 0.0; LI[j] = 0; }
+        for (int j = ln; j < 2 + 2 * (LE + L + 6) + (GROUPED ? LE + L : 0); j += L) SR[LE + L + j] = T(0);      // UA, UB (with guards), RC
+        for (int j = ln; j < NLA * WLp; j += L) Lb[j] = T(0);
+        for (int j = ln; j < WLp; j += L) { LW[2 * j] = T(0); LW[2 * j + 1] = T(0); LI[j] = 0; }
         __syncwarp();
         // rows n_lo-2, n_lo-1: from the (B,Nt,Nx) history with SAVE_STATE, else from the compact (B,2,Nx) carry buffer
         const int64_t row0 = save_state ? (int64_t)(qst[0] - 2) : 0;
-        const double *su = (const double *)a.state_u.ptr + (int64_t)b * a.state_u.bs + row0 * a.state_u.ts;
+        const T *su = (const T *)a.state_u.ptr + (int64_t)b * a.state_u.bs + row0 * a.state_u.ts;
 #pragma unroll
         for (int r = 0; r < ET; r++) {
             const int i = ln * ET + r;
-            S[u2o + PR(i)] = (i < NXT) ? su[i] : 0.0;
-            S[u1o + PR(i)] = (i < NXT) ? su[a.state_u.ts + i] : 0.0;
+            SR[u2o + PR(i)] = (i < NXT) ? su[i] : T(0);
+            SR[u1o + PR(i)] = (i < NXT) ? su[a.state_u.ts + i] : T(0);
         }
-        const double *sz = (const double *)a.state_z.ptr + (int64_t)b * a.state_z.bs + row0 * a.state_z.ts;
+        const T *sz = (const T *)a.state_z.ptr + (int64_t)b * a.state_z.bs + row0 * a.state_z.ts;
         for (int j = ln; j < WLa; j += L) {
-            Lb[z2o + j] = (j < NXL) ? sz[j] : 0.0;
-            Lb[z1o + j] = (j < NXL) ? sz[a.state_z.ts + j] : 0.0;
+            Lb[z2o + j] = (j < NXL) ? sz[j] : T(0);
+            Lb[z1o + j] = (j < NXL) ? sz[a.state_z.ts + j] : T(0);
         }
     }
     double uH1 = 0.0, uH2 = 0.0;
     if (Nt > 2) {
         const int n_lo = qst[0];
-        if (a.u_H.ptr || n_lo == 2) { uH2 = ctl_uH(A, b, n_lo - 2); uH1 = ctl_uH(A, b, n_lo - 1); }
+        if (a.u_H.ptr || n_lo == 2) { uH2 = ctl_uH<T>(A, b, n_lo - 2); uH1 = ctl_uH<T>(A, b, n_lo - 1); }
         else { uH2 = A.uH_carry[2 * (int64_t)b]; uH1 = A.uH_carry[2 * (int64_t)b + 1]; }     // handed over by the previous time slice
     }
     uint32_t cnt_outer = 0, cnt_sweeps = 0, cnt_ham = 0, cnt_steps = 0;
@@ -837,8 +908,8 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
             for (int s = ln; s < TB; s += L) {
                 const int n = n0 + s;
                 if (n >= n_hi) break;
-                if (!GROUPED && SFDTD_TAB_INLINE_I) fill_table_row_impl<GROUPED>(A, ti_, n, tab + s * NV, tabi + s * NI);
-                else fill_table_row<GROUPED>(A, ti_, n, tab + s * NV, tabi + s * NI);
+                if (!GROUPED && SFDTD_TAB_INLINE_I) fill_table_row_impl<T, GROUPED>(A, ti_, n, tab + s * NV, tabi + s * NI);
+                else fill_table_row<T, GROUPED>(A, ti_, n, tab + s * NV, tabi + s * NI);
             }
         }
         __syncwarp();
@@ -864,7 +935,7 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     interp_row(s_tl, i, N_l, i0, i1, w0, w1);
                     i0 = min(i0, WLa - 1) + 1; i1 = min(i1, WLa - 1) + 1;
                     if (i > N_t) { w1 = 0.f; i0 = 0; i1 = 0; }
-                    tix[r] = (i0 * 8) | ((i1 * 8) << 16); twb[r] = w1;          // byte offsets into a longitudinal row
+                    tix[r] = (i0 * TSZ) | ((i1 * TSZ) << 16); twb[r] = w1;      // byte offsets into a longitudinal row
                 }
                 for (int j = ln; j < WLp; j += L) {
                     int i0 = 0, i1 = 0; float w0 = 0.f, w1 = 0.f;
@@ -872,7 +943,7 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                         interp_row(s_lt, j, N_t, i0, i1, w0, w1);
                         i0 = PR(min(i0, LE - 1)); i1 = PR(min(i1, LE - 1));      // qs is PR()-indexed
                     }
-                    LW[2 * j] = (double)w0; LW[2 * j + 1] = (double)w1; LI[j] = (i0 * 8) | ((i1 * 8) << 16);     // byte offsets into qs
+                    LW[2 * j] = (T)w0; LW[2 * j + 1] = (T)w1; LI[j] = (i0 * TSZ) | ((i1 * TSZ) << 16);     // byte offsets into qs
                 }
                 curNt = N_t; curNl = N_l;
               }
@@ -880,61 +951,61 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
             }
 
             // ---- per-row coefficients, base right-hand side, factorisation ----
-            TriSolver<L, ET> ts;
-            double mu[ET + 1], rt[ET];
+            TriSolver<T, L, ET> ts;
+            T mu[ET + 1], rt[ET];
             const int i0row = ln * ET;
             const int lnp = ln * (ET + 1);
             auto PRL = [&](int c) { return lnp + c + (c + ET) / ET - 1; };    // PR(i0row + c) with the division folded at compile time
             {
-                double sq[ET + 1];
+                T sq[ET + 1];
                 {
                     // masked previous states (mask_1d, string.cpp:129-132): x * 0 keeps NaN like the reference's multiply
-                    double e1[ET + 4], e2[ET + 2];
+                    T e1[ET + 4], e2[ET + 2];
 #pragma unroll
-                    for (int r = 0; r < ET + 4; r++) { const int i = i0row + r - 2; e1[r] = S[u1o + PRL(r - 2)] * ((i <= N_t) ? 1.0 : 0.0); }
+                    for (int r = 0; r < ET + 4; r++) { const int i = i0row + r - 2; e1[r] = SR[u1o + PRL(r - 2)] * ((i <= N_t) ? T(1) : T(0)); }
 #pragma unroll
-                    for (int r = 0; r < ET + 2; r++) { const int i = i0row + r - 1; e2[r] = S[u2o + PRL(r - 1)] * ((i <= N_t) ? 1.0 : 0.0); }
+                    for (int r = 0; r < ET + 2; r++) { const int i = i0row + r - 1; e2[r] = SR[u2o + PRL(r - 1)] * ((i <= N_t) ? T(1) : T(0)); }
                     // Lambda = Dxb u1 (string.cpp:152) on the solved rows; mu = phi/h^2 Lambda; sq = phi/h^2 Lambda^2
-                    const double iht = t[T_IHT], ph2 = t[T_PH2];
+                    const T iht = (T)t[T_IHT], ph2 = (T)t[T_PH2];
 #pragma unroll
                     for (int r = 0; r <= ET; r++) {
                         const int i = i0row + r;
-                        const double lam = (i < R) ? (e1[r + 2] - e1[r + 1]) * iht : 0.0;
+                        const T lam = (i < R) ? (e1[r + 2] - e1[r + 1]) * iht : T(0);
                         mu[r] = ph2 * lam; sq[r] = mu[r] * lam;
                     }
                     // B11 u1 + C11 u2  (string.cpp:223-224)
-                    const double diagB = t[T_DIAGB], off1B = t[T_OFF1B], kh4 = t[T_KH4], diagC = t[T_DIAGC], offC = t[T_OFFC];
+                    const T diagB = (T)t[T_DIAGB], off1B = (T)t[T_OFF1B], kh4 = (T)t[T_KH4], diagC = (T)t[T_DIAGC], offC = (T)t[T_OFFC];
 #pragma unroll
                     for (int r = 0; r < ET; r++) {
                         const int i = i0row + r;
-                        double d4 = diagB;
+                        T d4 = diagB;
                         if (i == 1 || i == N_t - 1) d4 += kh4;          // Dxxxx_clamped (misc.cpp:146-163)
-                        const double Bu = d4 * e1[r + 2] + off1B * (e1[r + 1] + e1[r + 3]) + kh4 * (e1[r] + e1[r + 4]);
-                        const double Cu = diagC * e2[r + 1] + offC * (e2[r] + e2[r + 2]) + sq[r] * (e2[r + 1] - e2[r]) - sq[r + 1] * (e2[r + 2] - e2[r + 1]);
+                        const T Bu = d4 * e1[r + 2] + off1B * (e1[r + 1] + e1[r + 3]) + kh4 * (e1[r] + e1[r + 4]);
+                        const T Cu = diagC * e2[r + 1] + offC * (e2[r] + e2[r + 2]) + sq[r] * (e2[r + 1] - e2[r]) - sq[r + 1] * (e2[r + 2] - e2[r + 1]);
                         rt[r] = Bu + Cu;
                     }
                 }
                 // K_tl (2 z1 + z2)  (B12 = 2 K_tl, C12 = K_tl); the first coupling guess z = 2 z1 - z2 goes to ZA
                 {
-                    double yy[ET];
+                    T yy[ET];
 #pragma unroll
                     for (int r = 0; r < ET; r++) {
                         const int j0 = tix[r] & 0xffff, j1 = tix[r] >> 16;
                         const float w1f = twb[r];
-                        const double w1 = (double)w1f, w0 = (double)__fsub_rn(1.0f, w1f);
-                        yy[r] = w0 * (2.0 * ldb(Lb + z1o - 1, j0) + ldb(Lb + z2o - 1, j0)) + w1 * (2.0 * ldb(Lb + z1o - 1, j1) + ldb(Lb + z2o - 1, j1));
+                        const T w1 = (T)w1f, w0 = (T)__fsub_rn(1.0f, w1f);
+                        yy[r] = w0 * (T(2) * ldb(Lb + z1o - 1, j0) + ldb(Lb + z2o - 1, j0)) + w1 * (T(2) * ldb(Lb + z1o - 1, j1) + ldb(Lb + z2o - 1, j1));
                     }
-                    for (int j = ln; j < WLs; j += L) Lb[zao + j] = (j <= N_l) ? 2.0 * Lb[z1o + j] - Lb[z2o + j] : 0.0;
-                    double yyl = shup<L>(yy[ET - 1], 1);
-                    if (ln == 0) yyl = 0.0;
-                    double nub[ET + 1];
+                    for (int j = ln; j < WLs; j += L) Lb[zao + j] = (j <= N_l) ? T(2) * Lb[z1o + j] - Lb[z2o + j] : T(0);
+                    T yyl = shup<L>(yy[ET - 1], 1);
+                    if (ln == 0) yyl = T(0);
+                    T nub[ET + 1];
 #pragma unroll
                     for (int r = 0; r < ET; r++) nub[r] = mu[r] * (yy[r] - (r == 0 ? yyl : yy[r - 1]));
                     nub[ET] = shdn<L>(nub[0], 1);
-                    if (ln == L - 1) nub[ET] = 0.0;
+                    if (ln == L - 1) nub[ET] = T(0);
                     const int Rk = tabi[jj * NI + I_RK];
 #pragma unroll
-                    for (int r = 0; r < ET; r++) rt[r] = (i0row + r < Rk) ? (rt[r] + (nub[r] - nub[r + 1])) : 0.0;
+                    for (int r = 0; r < ET; r++) rt[r] = (i0row + r < Rk) ? (rt[r] + (nub[r] - nub[r + 1])) : T(0);
                 }
                 // manufactured solution (string.cpp:227-232): RHS -= f k^2 on every padded row, before the flat mask
                 MsStep ms;
@@ -945,21 +1016,21 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     const int Rk = tabi[jj * NI + I_RK];
                     const double two_ht = 2.0 / t[T_IHT];
 #pragma unroll
-                    for (int r = 0; r < ET; r++) if (i0row + r < Rk) rt[r] -= ms_row(ms, i0row + r, two_ht);
+                    for (int r = 0; r < ET; r++) if (i0row + r < Rk) rt[r] -= (T)ms_row(ms, i0row + r, two_ht);
                 }
                 // A11 (string.cpp:153-162), rows < R, tail folded into row R-1
                 {
-                    const double offA = t[T_OFFA], diagA = t[T_DIAGA], corr = t[T_CORR];
-                    double ca[ET], cb[ET], cc[ET];
+                    const T offA = (T)t[T_OFFA], diagA = (T)t[T_DIAGA], corr = (T)t[T_CORR];
+                    T ca[ET], cb[ET], cc[ET];
 #pragma unroll
                     for (int r = 0; r < ET; r++) {
                         const int i = i0row + r;
                         const bool in = i < R;
-                        ca[r] = (in && i > 0) ? offA - sq[r] : 0.0;
-                        cc[r] = (i + 1 < R) ? offA - sq[r + 1] : 0.0;
-                        double bb = diagA + sq[r] + sq[r + 1];
+                        ca[r] = (in && i > 0) ? offA - sq[r] : T(0);
+                        cc[r] = (i + 1 < R) ? offA - sq[r + 1] : T(0);
+                        T bb = diagA + sq[r] + sq[r + 1];
                         if (i == R - 1) bb -= corr;
-                        cb[r] = in ? bb : 1.0;
+                        cb[r] = in ? bb : T(1);
                     }
                     ts.factor(ca, cb, cc, ln);
                 }
@@ -970,26 +1041,27 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
 #pragma unroll
                     for (int r = 0; r < ET; r++) {
                         const int i = i0row + r;
-                        const double a2 = S[u2o + PRL(r)] * ((i <= N_t) ? 1.0 : 0.0), b2 = S[u2o + PRL(r - 1)] * ((i - 1 <= N_t) ? 1.0 : 0.0);
+                        const T a2 = SR[u2o + PRL(r)] * ((i <= N_t) ? T(1) : T(0)), b2 = SR[u2o + PRL(r - 1)] * ((i - 1 <= N_t) ? T(1) : T(0));
                         qs[PRL(r)] = mu[r] * (a2 - b2);
                     }
                     __syncwarp();
-                    const double ihl = t[T_IHL], ihl2 = ihl * ihl, s0k = t[T_S0K], s1k = t[T_S1K], ga2 = t[T_GA2], phl = t[T_PHL];
-                    const double dB = -2 + 2 * ga2 * ihl2, eB = -ga2 * ihl2;
-                    const double dC = (1 - s0k) - 2 * s1k * ihl2, eC = s1k * ihl2;
+                    const double ihl = t[T_IHL], ihl2 = ihl * ihl, s0k = t[T_S0K], s1k = t[T_S1K], ga2 = t[T_GA2];
+                    const T phl = (T)t[T_PHL];
+                    const T dB = (T)(-2 + 2 * ga2 * ihl2), eB = (T)(-ga2 * ihl2);
+                    const T dC = (T)((1 - s0k) - 2 * s1k * ihl2), eC = (T)(s1k * ihl2);
                     for (int j = ln; j < WLa; j += L) {
-                        double v = 0.0;
+                        T v = T(0);
                         if (j < keep_l && j < WLs) {
-                            const double z1c = (j <= N_l) ? Lb[z1o + j] : 0.0, z2c = (j <= N_l) ? Lb[z2o + j] : 0.0;
-                            const double z1l = (j - 1 <= N_l) ? Lb[z1o + j - 1] : 0.0, z1r = (j + 1 <= N_l) ? Lb[z1o + j + 1] : 0.0;
-                            const double z2l = (j - 1 <= N_l) ? Lb[z2o + j - 1] : 0.0, z2r = (j + 1 <= N_l) ? Lb[z2o + j + 1] : 0.0;
+                            const T z1c = (j <= N_l) ? Lb[z1o + j] : T(0), z2c = (j <= N_l) ? Lb[z2o + j] : T(0);
+                            const T z1l = (j - 1 <= N_l) ? Lb[z1o + j - 1] : T(0), z1r = (j + 1 <= N_l) ? Lb[z1o + j + 1] : T(0);
+                            const T z2l = (j - 1 <= N_l) ? Lb[z2o + j - 1] : T(0), z2r = (j + 1 <= N_l) ? Lb[z2o + j + 1] : T(0);
                             const int li0 = LI[j], li1 = LI[j + 1];
-                            const double pj = LW[2 * j] * ldb(qs, li0 & 0xffff) + LW[2 * j + 1] * ldb(qs, li0 >> 16);
-                            const double pj1 = LW[2 * j + 2] * ldb(qs, li1 & 0xffff) + LW[2 * j + 3] * ldb(qs, li1 >> 16);
+                            const T pj = LW[2 * j] * ldb(qs, li0 & 0xffff) + LW[2 * j + 1] * ldb(qs, li0 >> 16);
+                            const T pj1 = LW[2 * j + 2] * ldb(qs, li1 & 0xffff) + LW[2 * j + 3] * ldb(qs, li1 >> 16);
                             v = dB * z1c + eB * (z1l + z1r) + dC * z2c + eC * (z2l + z2r) - phl * (pj1 - pj);
                         }
                         // longitudinal rows sit at padded index Nx_t1 + j >= N_t + 1: x clamps to the right end
-                        if (manuf && j < keep_l && j < WLs) v -= ms_row(ms, NXT + j, 2.0 / t[T_IHT]);
+                        if (manuf && j < keep_l && j < WLs) v -= (T)ms_row(ms, NXT + j, 2.0 / t[T_IHT]);
                         Lb[rlo + j] = v;
                     }
                 }
@@ -997,15 +1069,15 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
             }
 
             // ---- block Gauss-Seidel solve of  A w = -(mr ; RL)  -> xs (registers), zfo (offset of the final z) ----
-            double xs[ET];
+            T xs[ET];
 #pragma unroll
-            for (int r = 0; r < ET; r++) xs[r] = 0.0;
+            for (int r = 0; r < ET; r++) xs[r] = T(0);
             int zfo = z1o;
             bool capped = false;                 // the block iteration of this step was cut at GS_CAP (diverging string)
             // All strings of a warp sweep until every one of them has converged (extra sweeps only tighten a
             // converged string), so the loop body carries no per-string predication.
-            auto gs_solve = [&](const double (&mr)[ET], bool need, bool first) {
-                bool conv = !need;
+            auto gs_solve = [&](const T (&mr)[ET], bool need, bool first) {
+                bool conv = !need || !valid;     // (a padding slot shadows a real string: it computes along but never holds the warp's sweep vote)
                 int sweeps = 0;
                 float e_prev = 0.f, isu = 0.f;
                 int zco = first ? zao : zfo;
@@ -1018,22 +1090,22 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                 do {
                     const int zno = (zco == zao) ? zbo : zao;
                     const bool chk = sweeps >= s_skip;                              // warp-uniform
-                    double d[ET];
+                    T d[ET];
                     {
-                        double y[ET];
+                        T y[ET];
 #pragma unroll
                         for (int r = 0; r < ET; r++) {
                             const int j0 = tix[r] & 0xffff, j1 = tix[r] >> 16;
                             const float w1f = twb[r];
-                            y[r] = (double)__fsub_rn(1.0f, w1f) * ldb(Lb + zco - 1, j0) + (double)w1f * ldb(Lb + zco - 1, j1);
+                            y[r] = (T)__fsub_rn(1.0f, w1f) * ldb(Lb + zco - 1, j0) + (T)w1f * ldb(Lb + zco - 1, j1);
                         }
-                        double yl = shup<L>(y[ET - 1], 1);
-                        if (ln == 0) yl = 0.0;
-                        double nuc[ET + 1];
+                        T yl = shup<L>(y[ET - 1], 1);
+                        if (ln == 0) yl = T(0);
+                        T nuc[ET + 1];
 #pragma unroll
                         for (int r = 0; r < ET; r++) nuc[r] = mu[r] * (y[r] - (r == 0 ? yl : y[r - 1]));
                         nuc[ET] = shdn<L>(nuc[0], 1);
-                        if (ln == L - 1) nuc[ET] = 0.0;
+                        if (ln == L - 1) nuc[ET] = T(0);
 #pragma unroll
                         for (int r = 0; r < ET; r++) d[r] = (nuc[r + 1] - nuc[r]) - mr[r];
                     }
@@ -1056,23 +1128,24 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
 #pragma unroll
                     for (int r = 0; r < ET; r++) if (upd) xs[r] = d[r];
                     // q = mu (x_i - x_{i-1})  (the scale phi/h_t^2 and the 1/h_t of Dxb are folded into T_PHL)
-                    double xl = shup<L>(xs[ET - 1], 1);
-                    if (ln == 0) xl = 0.0;
+                    T xl = shup<L>(xs[ET - 1], 1);
+                    if (ln == 0) xl = T(0);
 #pragma unroll
                     for (int r = 0; r < ET; r++) qs[PRL(r)] = mu[r] * (xs[r] - (r == 0 ? xl : xs[r - 1]));
                     __syncwarp();
                     // P = Int_lt q is evaluated where it is used (rows j and j+1): one shared-memory round trip and one warp
                     // barrier fewer per sweep than staging P
                     {
-                        const double PHL = t[T_PHL], idA = t[T_IDA], eidA = t[T_EIDA];
+                        const T PHL = (T)t[T_PHL], idA = (T)t[T_IDA], eidA = (T)t[T_EIDA];
+                        typedef typename Vec2<T>::type T2;
                         if (upd) for (int j = ln; j < WLs; j += L) {
                             const int li0 = LI[j], li1 = LI[j + 1];
-                            const double2 w0 = *(const double2 *)(LW + 2 * j), w1 = *(const double2 *)(LW + 2 * j + 2);
-                            const double pj = w0.x * ldb(qs, li0 & 0xffff) + w0.y * ldb(qs, li0 >> 16);
-                            const double pj1 = w1.x * ldb(qs, li1 & 0xffff) + w1.y * ldb(qs, li1 >> 16);
-                            double rhs = PHL * (pj1 - pj);
+                            const T2 w0 = *(const T2 *)(LW + 2 * j), w1 = *(const T2 *)(LW + 2 * j + 2);
+                            const T pj = w0.x * ldb(qs, li0 & 0xffff) + w0.y * ldb(qs, li0 >> 16);
+                            const T pj1 = w1.x * ldb(qs, li1 & 0xffff) + w1.y * ldb(qs, li1 >> 16);
+                            T rhs = PHL * (pj1 - pj);
                             if (j < keep_l) rhs -= Lb[rlo + j];
-                            const double zr = (j + 1 < WLs) ? Lb[zco + j + 1] : 0.0;
+                            const T zr = (j + 1 < WLs) ? Lb[zco + j + 1] : T(0);
                             Lb[zno + j] = rhs * idA - eidA * (Lb[zco + j - 1] + zr);
                         }
                     }
@@ -1082,12 +1155,12 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     bool ok = false;
                     if (chk) {
                         if (!have_su) {
-                            const float suf = hi_to_float(red_maxu<L>(su));
+                            const float suf = hi_to_float<T>(red_maxu<L>(su));
                             isu = __fdividef(1.0f, suf);                            // 1/0 = inf: (0 * inf) = NaN ends the sweeps below
                             dead = !(suf < INFINITY);                               // NaN / inf state: nothing left to converge
                             have_su = true;
                         }
-                        if (sweeps > 1) e = hi_to_float(red_maxu<L>(du)) * isu;      // relative change of the transverse block in this sweep
+                        if (sweeps > 1) e = hi_to_float<T>(red_maxu<L>(du)) * isu;   // relative change of the transverse block in this sweep
                         if (sweeps == 1) {
                             ok = dead;
                         } else {
@@ -1095,7 +1168,7 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                             // The longitudinal block is an affine image of the transverse one (z = A22^-1(-r_l - K_lt x), Jacobi
                             // error contracts by 2e-5 per sweep), so it needs no criterion of its own.
                             float rho = 2.0f * rho_h;
-                            if (sweeps >= 3 && prev_chk) {
+                            if (sweeps >= 3 && prev_chk && e_prev > Real<T>::RATE_MIN) {
                                 // measured contraction rate e / e_prev (e_prev = 0: the iteration had already converged)
                                 const float rr = __fdividef(e, fmaxf(e_prev, 1e-37f));
                                 const float rh = (rr > rho_h) ? rr : 0.5f * (rho_h + rr);
@@ -1106,8 +1179,8 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                             // e rho / (1 - rho) <= tol, without the division
                             // (a warm-started re-solve of a later fixed-point pass starts from the previous pass's solution: its
                             // very first change is already a meaningful error measure)
-                            ok = (sweeps >= ((keep_l > 0) ? 4 : (first ? 3 : 2))) && !(e * rho > GS_TOL * (1.0f - rho));
-                            ok = ok || !(e < INFINITY) || dead;
+                            ok = (sweeps >= ((keep_l > 0) ? SFDTD_MIN_SW_L : (first ? SFDTD_MIN_SW : 2))) && !(e * rho > GS_TOL * (1.0f - rho));
+                            ok = ok || !(e < INFINITY) || dead || (sizeof(T) == 4 && sweeps >= 2 && e <= Real<T>::E_FLOOR);
                             e_prev = e;
                             if (sweeps >= GS_CAP && !ok && !conv) { status |= SFDTD_ST_SOLVER_CAP; capped = true; ok = true; }
                         }
@@ -1119,18 +1192,19 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                 zfo = zco;
             };
 
-            double vrel = 0.0, FH = 0.0, uH = 0.0;
-            double bnum = 0.0, bden = 0.0;
-            double nu[ET];
+            T vrel = T(0);
+            double FH = 0.0, uH = 0.0;
+            T bnum = T(0), bden = T(0);
+            T nu[ET];
 
             // ---- bow: raised-cosine weights over the Nx_t1-point axis (bow.cpp:32, misc.cpp:20-34) ----
             // window rows bow_ic + c*L + ln (c = 0, 1); bow_o[c] = this lane's normalised weights; bow_S = normaliser
-            double bow_o[2] = {0.0, 0.0}, bow_S = 1.0; int bow_ic = 0;
+            T bow_o[2] = {T(0), T(0)}; double bow_S = 1.0; int bow_ic = 0;
             auto bow_window = [&]() {
                 const double ctr = t[T_CTR], wid = t[T_WID];
                 const double hw = wid * 0.5;
                 bow_ic = tabi[jj * NI + I_IC];
-                double acc = 0.0;
+                double acc = 0.0, bo[2];
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
                     const int i = bow_ic + c * L + ln;
@@ -1143,18 +1217,19 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                         else if (p != p) o = p;
                     }
                     if (((c == 1 && ln == L - 1) || i >= LE) && o != 0.0) status |= SFDTD_ST_BOW_WINDOW;
-                    bow_o[c] = o; acc += fabs(o);
+                    bo[c] = o; acc += fabs(o);
                 }
                 bow_S = red_sum<L>(acc);
-                bow_o[0] = bow_o[0] / bow_S; bow_o[1] = bow_o[1] / bow_S;      // 0/0 -> NaN like the reference
+                bow_o[0] = (T)(bo[0] / bow_S); bow_o[1] = (T)(bo[1] / bow_S);  // 0/0 -> NaN like the reference
             };
-            const double ik = A.ik, k2 = A.k2;
+            const double k2 = A.k2;
+            const T ik = (T)A.ik;
 
             if (!GROUPED) {
                 // ================= independent mode: unforced string, one solve =================
                 // v_r of an un-bowed string (the reference evaluates it for every string, bow.cpp:35-38): the raised-cosine
                 // window weights are computed before the solve, branch-free, so that their latency overlaps with it
-                double bw0 = 0.0, bw1 = 0.0;
+                T bw0 = T(0), bw1 = T(0);
                 if (do_bow) {
                     const double ctr = t[T_CTR], wid = t[T_WID];
                     const double hw = wid * 0.5, iw2 = 2.0 * frcp(wid);
@@ -1164,9 +1239,10 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                         const double x = (double)xaxs[min(i, NXT - 1)];
                         const double dm = __dsub_rn(__dsub_rn(x, ctr), hw), dp = __dadd_rn(__dsub_rn(x, ctr), hw);
                         const double p = __dmul_rn(-dm, dp);
-                        double o = 0.5 * (1.0 + cospi((x - ctr) * iw2));
-                        o = (p > 0 && i < NXT) ? o : ((p != p && i < NXT) ? p : 0.0);
-                        if (((c == 1 && ln == L - 1) || i >= LE) && o != 0.0) status |= SFDTD_ST_BOW_WINDOW;
+                        // (window membership in double in every build; the weight itself in the build's arithmetic)
+                        T o = T(0.5) * (T(1) + t_cospi((T)((x - ctr) * iw2)));
+                        o = (p > 0 && i < NXT) ? o : ((p != p && i < NXT) ? (T)p : T(0));
+                        if (((c == 1 && ln == L - 1) || i >= LE) && o != T(0)) status |= SFDTD_ST_BOW_WINDOW;
                         return o;
                     };
                     bw0 = window(0);
@@ -1181,12 +1257,12 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                 for (int r = 0; r < ET; r++) {
                     const int i = i0row + r;
                     const bool keep = (i < N_t) && (i != 0) && (i < R);
-                    nu[r] = keep ? xs[r] : xs[r] * 0.0;
+                    nu[r] = keep ? xs[r] : xs[r] * T(0);
                 }
                 if (do_bow) {
                     // v_rel of the last pass: sum rc_i ((u_i - u1_i)/k - v_b), rc = o / sum|o|  ==  (sum o_i d_i) / (k sum o) - v_b
 #pragma unroll
-                    for (int r = 0; r < ET; r++) { const int i = i0row + r; qs[PRL(r)] = nu[r] - S[u1o + PRL(r)] * ((i <= N_t) ? 1.0 : 0.0); }
+                    for (int r = 0; r < ET; r++) { const int i = i0row + r; qs[PRL(r)] = nu[r] - SR[u1o + PRL(r)] * ((i <= N_t) ? T(1) : T(0)); }
                     __syncwarp();
                     const int wi0 = min(bow_ic + ln, LE - 1), wi1 = min(bow_ic + L + ln, LE - 1);
                     bnum = bw0 * qs[PR(wi0)] + bw1 * qs[PR(wi1)]; bden = fabs(bw0) + fabs(bw1);     // reduced with the readout sums below
@@ -1196,8 +1272,8 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     // un-hammered string: the contact loop runs once with eta = 0 (hammer.cpp:28-53)
                     const int idxH = tabi[jj * NI + I_IDXH];
                     const double mk = (idxH <= N_t) ? 1.0 : 0.0;
-                    const double eta1 = uH1 - S[u1o + PR(idxH)] * mk;
-                    const double eta2 = uH2 - S[u2o + PR(idxH)] * mk;
+                    const double eta1 = uH1 - (double)SR[u1o + PR(idxH)] * mk;
+                    const double eta2 = uH2 - (double)SR[u2o + PR(idxH)] * mk;
                     const double r1 = eta1 > 0 ? eta1 : (eta1 != eta1 ? eta1 : 0.0);
                     const double ex = cst[C_AHM1];
                     const double r1pow = (ex == 2.0) ? r1 * r1 : ((ex == 0.0) ? 1.0 : pow(r1, ex));
@@ -1218,7 +1294,7 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     bow_window();
                     rc_nan = (bow_S == 0.0) || (bow_S != bow_S);             // every weight is NaN (0/0) in the reference
 #pragma unroll
-                    for (int r = 0; r < ET; r++) RC[PRL(r)] = 0.0;
+                    for (int r = 0; r < ET; r++) RC[PRL(r)] = T(0);
                     __syncwarp();
                     if (bow_ic + ln < LE) RC[PR(bow_ic + ln)] = bow_o[0];
                     if (bow_ic + L + ln < LE) RC[PR(bow_ic + L + ln)] = bow_o[1];
@@ -1228,16 +1304,17 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                 double eta1 = 0.0, eta2 = 0.0, r1pow = 0.0;
                 if (do_ham) {
                     const double mk = (idxH <= N_t) ? 1.0 : 0.0;
-                    eta1 = uH1 - S[u1o + PR(idxH)] * mk;
-                    eta2 = uH2 - S[u2o + PR(idxH)] * mk;
+                    eta1 = uH1 - (double)SR[u1o + PR(idxH)] * mk;
+                    eta2 = uH2 - (double)SR[u2o + PR(idxH)] * mk;
                     const double r1 = eta1 > 0 ? eta1 : (eta1 != eta1 ? eta1 : 0.0);
                     const double ex = cst[C_AHM1];
                     r1pow = (ex == 2.0) ? r1 * r1 : ((ex == 0.0) ? 1.0 : pow(r1, ex));
                 }
-                const double tol_t = GROUPED ? t[T_TOLT] : 0.0, tol_l = GROUPED ? t[T_TOLL] : 0.0;
+                const double tol_t = GROUPED ? t[T_TOLT] : 0.0;
+                const T tol_tT = (T)tol_t, tol_l = GROUPED ? (T)t[T_TOLL] : T(0);
                 // the iterate starts as the unmasked state[n-1] (string.cpp:190-191)
 #pragma unroll
-                for (int r = 0; r < ET; r++) nu[r] = S[u1o + PRL(r)];
+                for (int r = 0; r < ET; r++) nu[r] = SR[u1o + PRL(r)];
                 for (int j = ln; j < WLa; j += L) Lb[zpo + j] = Lb[z1o + j];
                 __syncwarp();
                 // hammer contact loop (hammer.cpp:28-53).  Every string iterates its own scalar loop; only the exit test is an
@@ -1249,7 +1326,7 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                 double eps_u = 0.0;
                 unsigned hgm = 0;                  // exit-test bits of the coming contact loop, OR-ed over the group
                 if (GROUPED && group_has_hammer) {
-                    eps_u = fetch_row<L, ET>(nu, idxH);
+                    eps_u = (double)fetch_row<L, ET>(nu, idxH);
                     // (normally the mask already came with the last vote of the previous step, see below)
                     if (have_next) hgm = hgm_next;
                     else hgm = gc.vote((valid ? ham_mask(hin, eta1 * hm, eps_u) : 0u) << 1) >> 1;
@@ -1261,23 +1338,24 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     // bow force (bow.cpp:35-40)
                     double hb = 0.0;
                     if (do_bow) {
-                        const double vB = t[T_VB];
-                        double acc = 0.0;
+                        const T vB = (T)t[T_VB];
+                        T acc = T(0);
 #pragma unroll
                         for (int r = 0; r < ET; r++) {
                             const int i = i0row + r;
-                            const double mk = (i <= N_t) ? 1.0 : 0.0;
-                            const double m1 = S[u1o + PRL(r)] * mk;
-                            const double dd = (iter == 0) ? (m1 - S[u2o + PRL(r)] * mk) : (nu[r] - m1);
-                            const double rcv = rc_nan ? bow_o[0] : RC[PRL(r)];
+                            const T mk = (i <= N_t) ? T(1) : T(0);
+                            const T m1 = SR[u1o + PRL(r)] * mk;
+                            const T dd = (iter == 0) ? (m1 - SR[u2o + PRL(r)] * mk) : (nu[r] - m1);
+                            const T rcv = rc_nan ? bow_o[0] : RC[PRL(r)];
                             acc += rcv * (dd * ik - vB);
                         }
                         vrel = red_sum<L>(acc);
                         // the friction curve only enters the right-hand side of bowed strings (string.cpp:225)
                         if (bowm) {
-                            const double sg = (vrel > 0) ? 1.0 : ((vrel < 0) ? -1.0 : 0.0);
+                            const double vr = (double)vrel;
+                            const double sg = (vr > 0) ? 1.0 : ((vr < 0) ? -1.0 : 0.0);
                             const double phi0 = cst[C_PHI0], phi1 = cst[C_PHI1];
-                            hb = (vrel != vrel) ? vrel : sg * (phi1 + (1 - phi1) * exp(-phi0 * fabs(vrel)));
+                            hb = (vr != vr) ? vr : sg * (phi1 + (1 - phi1) * exp(-phi0 * fabs(vr)));
                         }
                     }
                     // hammer loop (hammer.cpp:28-53); its exit test is an any-over-batch vote
@@ -1309,16 +1387,16 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     // ---- linear solve  A w = -(RHS)  ----
                     const bool need = !solved || forced;
                     if (__any_sync(FULLMASK, need)) {
-                        double mr[ET];
-                        const double sB = -k2 * ((GROUPED ? t[T_FB] : 0.0) * hb) * t[T_IHT];
-                        const double sH = hamm ? nan0(-k2 * (cst[C_MR] * FH)) : 0.0;
+                        T mr[ET];
+                        const T sB = (T)(-k2 * ((GROUPED ? t[T_FB] : 0.0) * hb) * t[T_IHT]);
+                        const T sH = hamm ? (T)nan0(-k2 * (cst[C_MR] * FH)) : T(0);
 #pragma unroll
                         for (int r = 0; r < ET; r++) {
                             const int i = i0row + r;
-                            double f = 0.0;
+                            T f = T(0);
                             if (bowm) f += nan0(sB * (rc_nan ? bow_o[0] : RC[PRL(r)]));
                             if (hamm && i == idxH) f += sH;
-                            mr[r] = (i < Rk) ? rt[r] + f : 0.0;
+                            mr[r] = (i < Rk) ? rt[r] + f : T(0);
                         }
                         gs_solve(mr, need, !solved);
                         solved = true;
@@ -1329,18 +1407,18 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     for (int r = 0; r < ET; r++) {
                         const int i = i0row + r;
                         const bool keep = (i < N_t) && (i != 0) && (i < R);
-                        const double nv = keep ? xs[r] : xs[r] * 0.0;
-                        const double df = fabs(nu[r] - nv);
+                        const T nv = keep ? xs[r] : xs[r] * T(0);
+                        const T df = fabs(nu[r] - nv);
                         nan_u |= (df != df);
-                        nc_t |= (df > tol_t);
+                        nc_t |= (df > tol_tT);
                         nu[r] = nv;
                     }
                     int nc_l = 0, nan_z = 0;
                     for (int j = ln; j < WLa; j += L) {
                         const bool keep = (j < N_l) && (j != 0) && (j < WLs);
-                        const double zs = (j < WLs) ? Lb[zfo + j] : 0.0;
-                        const double zv = keep ? zs : zs * 0.0;
-                        const double df = fabs(Lb[zpo + j] - zv);
+                        const T zs = (j < WLs) ? Lb[zfo + j] : T(0);
+                        const T zv = keep ? zs : zs * T(0);
+                        const T df = fabs(Lb[zpo + j] - zv);
                         nan_z |= (df != df);
                         nc_l |= (df > tol_l);
                         Lb[zpo + j] = zv;
@@ -1356,7 +1434,7 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     bool spec = false;
                     if (GROUPED && group_has_hammer) {
                         // exit tests of the next pass's contact loop (contact-point displacement of the new iterate) ride along ...
-                        eps_u = fetch_row<L, ET>(nu, idxH);
+                        eps_u = (double)fetch_row<L, ET>(nu, idxH);
                         if (valid) word |= ham_mask(hin, eta1 * hm, eps_u) << 1;
                         // ... and so do those of the NEXT STEP's first contact loop, in case this pass turns out to be the last
                         // one of the step: everything they need (new state row, hammer displacement of this pass, the next
@@ -1368,7 +1446,7 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                             const int idxHn = tin[I_IDXH];
                             const double mkn = (idxHn <= tin[I_NT]) ? 1.0 : 0.0;
                             const double uH1n = t[T_UHPRE] + (out_ham ? uH : 0.0);
-                            const double u1n = fetch_row<L, ET>(nu, idxHn), u2n = S[u1o + PR(idxHn)];
+                            const double u1n = (double)fetch_row<L, ET>(nu, idxHn), u2n = (double)SR[u1o + PR(idxHn)];
                             HamIn hn;
                             hn.eta1 = uH1n - u1n * mkn; hn.eta2 = uH1 - u2n * mkn;
                             const double r1n = hn.eta1 > 0 ? hn.eta1 : (hn.eta1 != hn.eta1 ? hn.eta1 : 0.0);
@@ -1389,28 +1467,28 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
             cnt_steps += 1;
 
             // ---- save and readout (string.cpp:263-303) ----
-            double uo, zo;
+            T uo, zo;
             {
                 // new longitudinal row (masked, Dirichlet) into the oldest buffer; surface integral on the fly
                 const int zno = z2o;
-                const double rdw = t[T_RDW];
-                double acc = 0.0;
+                const T rdw = (T)t[T_RDW];
+                T acc = T(0);
                 const int hi = max(max(ext1, ext2), WLs);
                 if (GROUPED) {
-                    for (int j = ln; j < hi; j += L) { const double zv = Lb[zpo + j]; acc += (zv - Lb[z1o + j]) * rdw; Lb[zno + j] = zv; }
+                    for (int j = ln; j < hi; j += L) { const T zv = Lb[zpo + j]; acc += (zv - Lb[z1o + j]) * rdw; Lb[zno + j] = zv; }
                 } else {
                     for (int j = ln; j < hi; j += L) {
                         const bool keep = (j < N_l) && (j != 0) && (j < WLs);
-                        const double zs = (j < WLs) ? Lb[zfo + j] : 0.0;
-                        const double zv = keep ? zs : zs * 0.0;
+                        const T zs = (j < WLs) ? Lb[zfo + j] : T(0);
+                        const T zv = keep ? zs : zs * T(0);
                         acc += (zv - Lb[z1o + j]) * rdw; Lb[zno + j] = zv;
                     }
                 }
                 ext2 = ext1; ext1 = WLs;
                 if (surf) {
-                    double au = 0.0;
+                    T au = T(0);
 #pragma unroll
-                    for (int r = 0; r < ET; r++) au += (nu[r] - S[u1o + PRL(r)]) * rdw;
+                    for (int r = 0; r < ET; r++) au += (nu[r] - SR[u1o + PRL(r)]) * rdw;
                     // one butterfly for all sums of the step (independent shuffles overlap)
 #pragma unroll
                     for (int o = L / 2; o > 0; o >>= 1) {
@@ -1423,33 +1501,33 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
                     __syncwarp();
                     const double rp = cst[C_RP];
                     const int ui = 1 + (int)floor(__dmul_rn((double)N_t, rp));
-                    const double uf = 1 + rp * t[T_IHT] - (double)ui;
+                    const T uf = (T)(1 + rp * t[T_IHT] - (double)ui);
                     const int zi = 1 + (int)floor(__dmul_rn((double)N_l, rp));
-                    const double zf = 1 + rp * t[T_IHL] - (double)zi;
-                    const double ua = fetch_row<L, ET>(nu, ui), ub = fetch_row<L, ET>(nu, ui + 1);
-                    uo = (1 - uf) * ua + uf * ub;
-                    const double za = (zi < WLa) ? Lb[zno + zi] : 0.0, zb = (zi + 1 < WLa) ? Lb[zno + zi + 1] : 0.0;
-                    zo = (1 - zf) * za + zf * zb;
+                    const T zf = (T)(1 + rp * t[T_IHL] - (double)zi);
+                    const T ua = fetch_row<L, ET>(nu, ui), ub = fetch_row<L, ET>(nu, ui + 1);
+                    uo = (T(1) - uf) * ua + uf * ub;
+                    const T za = (zi < WLa) ? Lb[zno + zi] : T(0), zb = (zi + 1 < WLa) ? Lb[zno + zi + 1] : T(0);
+                    zo = (T(1) - zf) * za + zf * zb;
                 }
-                if (!GROUPED && do_bow) vrel = (bnum * A.ik) / bden - t[T_VB];      // empty window: 0/0 = NaN like the reference
+                if (!GROUPED && do_bow) vrel = (bnum * ik) / bden - (T)t[T_VB];     // empty window: 0/0 = NaN like the reference
                 // state rows: state[:, n] += u  (in place, onto pre-loaded content; string.cpp:264-265)
                 if (save_state) {
-                    double *su = (double *)a.state_u.ptr + (int64_t)b * a.state_u.bs + (int64_t)n * a.state_u.ts;
+                    T *su = (T *)a.state_u.ptr + (int64_t)b * a.state_u.bs + (int64_t)n * a.state_u.ts;
 #pragma unroll
                     for (int r = 0; r < ET; r++) {
                         const int i = i0row + r;
                         // (spare slots shadow a real string: they must not read rows its owner is writing)
                         if (i < NXT && valid) { nu[r] += su[i]; su[i] = nu[r]; }
                     }
-                    double *sz = (double *)a.state_z.ptr + (int64_t)b * a.state_z.bs + (int64_t)n * a.state_z.ts;
+                    T *sz = (T *)a.state_z.ptr + (int64_t)b * a.state_z.bs + (int64_t)n * a.state_z.ts;
                     __syncwarp();
                     for (int j = ln; j < WLa; j += L) {
-                        if (j < NXL && valid) { const double row = Lb[zno + j] + sz[j]; sz[j] = row; Lb[zno + j] = row; }
+                        if (j < NXL && valid) { const T row = Lb[zno + j] + sz[j]; sz[j] = row; Lb[zno + j] = row; }
                     }
                     ext1 = WLa;
                 }
 #pragma unroll
-                for (int r = 0; r < ET; r++) S[u2o + PRL(r)] = nu[r];
+                for (int r = 0; r < ET; r++) SR[u2o + PRL(r)] = nu[r];
                 { const int tmp = u1o; u1o = u2o; u2o = tmp; }
                 z2o = z1o; z1o = zno;
                 __syncwarp();
@@ -1458,7 +1536,7 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
             uH2 = uH1; uH1 = uHtot;
             if (ln == 0) {
                 double *o = ost + jj * NOUT;
-                o[0] = uo; o[1] = zo; o[2] = out_bow ? vrel : 0.0; o[3] = out_ham ? FH : 0.0; o[4] = uHtot;
+                o[0] = (double)uo; o[1] = (double)zo; o[2] = out_bow ? (double)vrel : 0.0; o[3] = out_ham ? FH : 0.0; o[4] = uHtot;
             }
         }
         // ---- flush staged outputs: lane s writes step n0+s (coalesced rows) ----
@@ -1468,12 +1546,12 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
             for (int s = ln; s < jmax; s += L) {
                 const int n = n0 + s;
                 const double *o = ost + s * NOUT;
-                ((double *)a.uout.ptr)[(int64_t)b * a.uout.bs + (int64_t)n * a.uout.ts] = o[0];
-                ((double *)a.zout.ptr)[(int64_t)b * a.zout.bs + (int64_t)n * a.zout.ts] = o[1];
-                if (a.v_r.ptr) ((double *)a.v_r.ptr)[(int64_t)b * a.v_r.bs + (int64_t)n * a.v_r.ts] = o[2];
-                if (a.F_H.ptr) ((double *)a.F_H.ptr)[(int64_t)b * a.F_H.bs + (int64_t)n * a.F_H.ts] = o[3];
-                if (a.u_H.ptr) ((double *)a.u_H.ptr)[(int64_t)b * a.u_H.bs + (int64_t)n * a.u_H.ts] = o[4];
-                if (a.u_H_out.ptr) ((double *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)n * a.u_H_out.ts] = o[4] * ik;
+                ((T *)a.uout.ptr)[(int64_t)b * a.uout.bs + (int64_t)n * a.uout.ts] = (T)o[0];
+                ((T *)a.zout.ptr)[(int64_t)b * a.zout.bs + (int64_t)n * a.zout.ts] = (T)o[1];
+                if (a.v_r.ptr) ((T *)a.v_r.ptr)[(int64_t)b * a.v_r.bs + (int64_t)n * a.v_r.ts] = (T)o[2];
+                if (a.F_H.ptr) ((T *)a.F_H.ptr)[(int64_t)b * a.F_H.bs + (int64_t)n * a.F_H.ts] = (T)o[3];
+                if (a.u_H.ptr) ((T *)a.u_H.ptr)[(int64_t)b * a.u_H.bs + (int64_t)n * a.u_H.ts] = (T)o[4];
+                if (a.u_H_out.ptr) ((T *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)n * a.u_H_out.ts] = (T)(o[4] * ik);
             }
         }
         __syncwarp();
@@ -1483,18 +1561,18 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
     const uint32_t status_all = (uint32_t)red_or<L>((int)status);
     if (valid) {
         if (!save_state && Nt > 2) {
-            double *su = (double *)a.state_u.ptr + (int64_t)b * a.state_u.bs;
+            T *su = (T *)a.state_u.ptr + (int64_t)b * a.state_u.bs;
 #pragma unroll
             for (int r = 0; r < ET; r++) {
                 const int i = ln * ET + r;
-                if (i < NXT) { su[i] = S[u2o + PR(i)]; su[a.state_u.ts + i] = S[u1o + PR(i)]; }
+                if (i < NXT) { su[i] = SR[u2o + PR(i)]; su[a.state_u.ts + i] = SR[u1o + PR(i)]; }
             }
-            double *sz = (double *)a.state_z.ptr + (int64_t)b * a.state_z.bs;
+            T *sz = (T *)a.state_z.ptr + (int64_t)b * a.state_z.bs;
             for (int j = ln; j < WLa; j += L) if (j < NXL) { sz[j] = Lb[z2o + j]; sz[a.state_z.ts + j] = Lb[z1o + j]; }
         }
         // u_H_out / u_H columns 0,1 (simulator.cpp:57 divides the whole tensor)
         if (ln < 2 && ln < Nt && qst[0] == 2 && a.u_H_out.ptr) {
-            ((double *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)ln * a.u_H_out.ts] = ctl_uH(A, b, ln) * A.ik;
+            ((T *)a.u_H_out.ptr)[(int64_t)b * a.u_H_out.bs + (int64_t)ln * a.u_H_out.ts] = (T)(ctl_uH<T>(A, b, ln) * A.ik);
         }
         if (ln == 0 && !a.u_H.ptr && A.uH_carry) { A.uH_carry[2 * (int64_t)b] = uH2; A.uH_carry[2 * (int64_t)b + 1] = uH1; }
         if (ln == 0) {
@@ -1520,27 +1598,31 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
 }
 
 // independent mode: strings of unforced groups, any warp of any CTA
-template <int L, int ET, int MAXT, int MINB>
+template <typename T, int L, int ET, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_constant__ KArgs A) {
-    step_body<L, ET, false, false>(A, nullptr);
+    step_body<T, L, ET, false, false>(A, nullptr);
 }
 // grouped mode: one thread-block cluster of 128-thread CTAs per group; the CTA's descriptor picks the lane/row shape of its
 // string slots.  KIND 0: strings of <= 64 rows on 16 lanes x 4 rows, <= 128 rows on 32 lanes x 4 rows (168 registers, three
 // CTAs per SM -- of different groups, so that one group's barrier waits are filled by the others);  KIND 1: 32 lanes x 8 rows;
-// KIND 2: 32 lanes x 8 rows with the manufactured-solution forcing (vnv.cpp).
+// KIND 2: 32 lanes x 8 rows with the manufactured-solution forcing (vnv.cpp);  KIND 3: 32 lanes x 20 rows (strings of up to
+// 640 rows: f0 down to the reference's default floor of 27.5 Hz at 48 kHz; the row arrays of that shape exceed the register
+// file and partly live in local memory -- a coverage kernel, not a fast one).
 #ifndef SFDTD_GROUP_MINB
 #define SFDTD_GROUP_MINB 3
 #endif
-template <int KIND>
+template <typename T, int KIND>
 __global__ void __launch_bounds__(128, KIND == 0 ? SFDTD_GROUP_MINB : 1) sfdtd_group_kernel(const __grid_constant__ KArgs A) {
     const CtaDesc *cd = A.ctas + blockIdx.x;
     if (KIND == 0) {
-        if (cd->cls == 0) step_body<16, 4, true, false>(A, cd);
-        else step_body<32, 4, true, false>(A, cd);
+        if (cd->cls == 0) step_body<T, 16, 4, true, false>(A, cd);
+        else step_body<T, 32, 4, true, false>(A, cd);
     } else if (KIND == 1) {
-        step_body<32, 8, true, false>(A, cd);
+        step_body<T, 32, 8, true, false>(A, cd);
+    } else if (KIND == 2) {
+        step_body<T, 32, 8, true, true>(A, cd);
     } else {
-        step_body<32, 8, true, true>(A, cd);
+        step_body<T, 32, 20, true, false>(A, cd);
     }
 }
 
@@ -1557,15 +1639,15 @@ __global__ void sfdtd_synth_controls_kernel(const __grid_constant__ KArgs A, sfd
 }
 
 // ---- sfdtd_postprocess: NaN / silence flags, l-infinity gain, PCM quantisation (one CTA per string) ------------------
-template <int BITS>
+template <int BITS, typename T>
 __global__ void __launch_bounds__(256) sfdtd_postprocess_kernel(sfdtd_array U, sfdtd_array Z, int n0, int ns, double silence_db,
                                                                int normalize, uint8_t *is_nan, uint8_t *is_silent, double *gain_out,
                                                                uint8_t *pu, uint8_t *pz, uint8_t *pw, int64_t pitch) {
     const int b = blockIdx.x;
-    const double *u = (const double *)U.ptr + (int64_t)b * U.bs, *z = (const double *)Z.ptr + (int64_t)b * Z.bs;
+    const T *u = (const T *)U.ptr + (int64_t)b * U.bs, *z = (const T *)Z.ptr + (int64_t)b * Z.bs;
     double sq = 0.0, mx = 0.0; int nan = 0;
     for (int n = threadIdx.x; n < ns; n += blockDim.x) {
-        const double v = u[(int64_t)(n0 + n) * U.ts];
+        const double v = (double)u[(int64_t)(n0 + n) * U.ts];
         nan |= (v != v); sq += v * v; mx = fmax(mx, fabs(v));
     }
     __shared__ double s_sq[8], s_mx[8]; __shared__ int s_nan[8];
@@ -1599,7 +1681,7 @@ __global__ void __launch_bounds__(256) sfdtd_postprocess_kernel(sfdtd_array U, s
         for (int c = 0; c < 4; c++) {
             const int n = n4 + c;
             double uv = 0.0, zv = 0.0;
-            if (n < ns) { uv = u[(int64_t)(n0 + n) * U.ts]; zv = z[(int64_t)(n0 + n) * Z.ts]; }
+            if (n < ns) { uv = (double)u[(int64_t)(n0 + n) * U.ts]; zv = (double)z[(int64_t)(n0 + n) * Z.ts]; }
             qu[c] = q(gain * uv); qz[c] = q(gain * zv); qw[c] = q(gain * uv + gain * zv);
         }
         auto store = [&](uint8_t *base, const int (&v)[4]) {
@@ -1644,15 +1726,20 @@ __global__ void __launch_bounds__(256) sfdtd_fma_peak_kernel(T *out, int iters, 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 
+#ifndef SFDTD_F32_MINB
+#define SFDTD_F32_MINB 5            // CTAs per SM the small fp32 kernels are compiled for (register cap 65536 / (128 x MINB))
+#endif
 // independent-mode kernels: <=128-thread CTAs, a string needs rows <= L*ET; tier = kernel set
 // (tier 2, the default: 16 lanes x 4 rows for every string up to 64 rows, then 32x4, 32x8 -- measured fastest; tier 0 also
 // uses the 8-lane kernels, for A/B runs via SFDTD_TIER=0; 2- and 3-row kernels, tighter register caps (128) and a
 // REDUX-based max reduction all measured slower).
-struct Config { int L, ET, tier; void (*kern)(const KArgs); };
-#define CFG_I(L_, ET_, MB_, TIER_) Config{L_, ET_, TIER_, sfdtd_step_kernel<L_, ET_, 128, MB_>}
+// kern[dtype]: the fp64 build and (default tier only) the fp32 build; MB32_ = CTAs per SM the fp32 build is compiled for
+struct Config { int L, ET, tier; void (*kern[2])(const KArgs); };
+#define CFG_I(L_, ET_, MB_, TIER_) Config{L_, ET_, TIER_, {sfdtd_step_kernel<double, L_, ET_, 128, MB_>, nullptr}}
+#define CFG_D(L_, ET_, MB_, MB32_, TIER_) Config{L_, ET_, TIER_, {sfdtd_step_kernel<double, L_, ET_, 128, MB_>, sfdtd_step_kernel<float, L_, ET_, 128, MB32_>}}
 const Config g_configs[] = {   // smallest first
     CFG_I(8, 4, 3, 0), CFG_I(8, 6, 2, 0), CFG_I(16, 4, 3, 0), CFG_I(16, 6, 2, 0), CFG_I(32, 4, 3, 0), CFG_I(32, 8, 1, 0),
-    CFG_I(16, 4, 3, 2), CFG_I(32, 4, 3, 2), CFG_I(32, 8, 1, 2),
+    CFG_D(16, 4, 3, SFDTD_F32_MINB, 2), CFG_D(32, 4, 3, SFDTD_F32_MINB, 2), CFG_D(32, 8, 1, 2, 2), CFG_D(32, 12, 1, 1, 2), CFG_D(32, 20, 1, 1, 2),
     CFG_I(8, 4, 3, 3), CFG_I(16, 4, 3, 3), CFG_I(32, 4, 3, 3), CFG_I(32, 8, 1, 3),
 };
 #ifndef SFDTD_DEFAULT_TIER
@@ -1660,9 +1747,12 @@ const Config g_configs[] = {   // smallest first
 #endif
 constexpr int N_CONFIGS = sizeof(g_configs) / sizeof(g_configs[0]);
 // grouped-mode kernels and the slot shapes of their CTA classes
-void (*const g_group_kernels[3])(const KArgs) = {sfdtd_group_kernel<0>, sfdtd_group_kernel<1>, sfdtd_group_kernel<2>};
+void (*const g_group_kernels[2][4])(const KArgs) = {
+    {sfdtd_group_kernel<double, 0>, sfdtd_group_kernel<double, 1>, sfdtd_group_kernel<double, 2>, sfdtd_group_kernel<double, 3>},
+    {sfdtd_group_kernel<float, 0>, sfdtd_group_kernel<float, 1>, nullptr, sfdtd_group_kernel<float, 3>}};   // (no fp32 manufactured mode)
 struct GShape { int L, ET; };
-const GShape g_gshape[3][2] = {{{16, 4}, {32, 4}}, {{32, 8}, {32, 8}}, {{32, 8}, {32, 8}}};
+const GShape g_gshape[4][2] = {{{16, 4}, {32, 4}}, {{32, 8}, {32, 8}}, {{32, 8}, {32, 8}}, {{32, 20}, {32, 20}}};
+constexpr int MAX_ROWS = 640;       // transverse rows of the largest kernel shape (32 lanes x 20 rows)
 
 // longitudinal allocation classes of the independent mode (rows incl. the two guards)
 int wl_class(int rows, int c_min = 16) {
@@ -1672,8 +1762,8 @@ int wl_class(int rows, int c_min = 16) {
 }
 size_t xax_doubles(int NXT, bool need_xax) { return need_xax ? (size_t)((NXT + 3) / 4) * 2 : 0; }
 // independent mode: nslots strings with WLp longitudinal rows each
-size_t smem_bytes_indep(const Config &c, int nslots, int NXT, int WLp, bool need_xax) {
-    const size_t dbl = xax_doubles(NXT, need_xax) + (size_t)nslots * (slot_fixed_doubles(c.L, c.ET, false) + slot_long_doubles(WLp, false, c.L));
+size_t smem_bytes_indep(const Config &c, int nslots, int NXT, int WLp, bool need_xax, int tsz) {
+    const size_t dbl = xax_doubles(NXT, need_xax) + (size_t)nslots * (slot_fixed_doubles(c.L, c.ET, false, tsz) + slot_long_doubles(WLp, false, c.L, tsz));
     return dbl * sizeof(double) + 16;
 }
 int kernel_regs(void (*kern)(const KArgs)) {
@@ -1706,7 +1796,10 @@ int validate(const sfdtd_args *args) {
     if (!args) { snprintf(g_err, sizeof g_err, "args is NULL"); return SFDTD_ERR_ARG; }
     const sfdtd_args &a = *args;
     if (a.abi_version != SFDTD_ABI_VERSION) { snprintf(g_err, sizeof g_err, "abi_version %d != %d", a.abi_version, SFDTD_ABI_VERSION); return SFDTD_ERR_ARG; }
-    if (a.dtype != SFDTD_F64) { snprintf(g_err, sizeof g_err, "only SFDTD_F64 is built"); return SFDTD_ERR_UNSUPPORTED; }
+    if (a.dtype != SFDTD_F64 && a.dtype != SFDTD_F32) { snprintf(g_err, sizeof g_err, "dtype must be SFDTD_F64 or SFDTD_F32"); return SFDTD_ERR_UNSUPPORTED; }
+    if (a.dtype == SFDTD_F32 && (a.flags & SFDTD_MANUFACTURED)) {
+        snprintf(g_err, sizeof g_err, "the manufactured-solution mode is only built for SFDTD_F64"); return SFDTD_ERR_UNSUPPORTED;
+    }
     if (a.B <= 0 || a.group_size <= 0 || a.Nt < 0 || a.Nx_t1 <= 0 || a.Nx_l1 <= 0) { snprintf(g_err, sizeof g_err, "bad sizes"); return SFDTD_ERR_ARG; }
     const void *req[] = {a.state_u.ptr, a.state_z.ptr, a.kappa.ptr, a.alpha.ptr, a.pos.ptr, a.T60.ptr, a.phi_0.ptr, a.phi_1.ptr,
                          a.x_H.ptr, a.w_H.ptr, a.M_r.ptr, a.alpha_H.ptr, a.bow_mask, a.hammer_mask, a.xax, a.uout.ptr, a.zout.ptr,
@@ -1737,6 +1830,7 @@ void fill_kargs(KArgs &K, const sfdtd_args &a) {
     K.lamc = (double)a.lambda_c; K.order = (double)a.relative_order;
     K.mhd = (double)(-0.01f);                                                // hammer.cpp:3
     K.max_iter = a.max_iter > 0 ? a.max_iter : 100;
+    K.f32 = a.dtype == SFDTD_F32 ? 1 : 0;
 }
 
 // the device the call's memory lives on becomes the current device for the duration of the call
@@ -1760,7 +1854,7 @@ struct DeviceGuard {
 
 struct sfdtd_plan {
     int dev = 0, n_sms = 0;
-    int32_t B = 0, group_size = 0, Nt = 0, Nx_t1 = 0, Nx_l1 = 0, n_groups = 0;
+    int32_t B = 0, group_size = 0, Nt = 0, Nx_t1 = 0, Nx_l1 = 0, n_groups = 0, dtype = 0;
     uint32_t flags = 0;
     std::vector<Launch> launches;
     char *block = nullptr;           // one device allocation: maxNl | ids | ctas | queue words | width table | u_H carry
@@ -1864,7 +1958,8 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
     fill_kargs(K, a);
     P->verbose = getenv("SFDTD_VERBOSE") != nullptr;
     P->B = a.B; P->group_size = a.group_size; P->Nt = a.Nt; P->Nx_t1 = a.Nx_t1; P->Nx_l1 = a.Nx_l1; P->n_groups = n_groups;
-    P->flags = a.flags;
+    P->flags = a.flags; P->dtype = a.dtype;
+    const int dt = a.dtype == SFDTD_F32 ? 1 : 0, tsz = dt ? 4 : 8;
 
     CK(guard.enter(a.state_u.ptr));
     CK(cudaGetDevice(&P->dev));
@@ -1884,7 +1979,8 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
     // ---- prepass: per-string grid maxima and difficulty estimate; ONE device->host read ----
     CK(cudaMallocAsync((void **)&d_max, sizeof(int32_t) * 2 * (size_t)a.B, stream));
     CK(cudaMallocAsync((void **)&d_est, sizeof(float) * (size_t)a.B, stream));
-    sfdtd_prepass_kernel<<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B, d_est);
+    if (dt) sfdtd_prepass_kernel<float><<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B, d_est);
+    else sfdtd_prepass_kernel<double><<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B, d_est);
     g_launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h_max.data(), d_max, sizeof(int32_t) * 2 * (size_t)a.B, cudaMemcpyDeviceToHost, stream));
@@ -1912,7 +2008,7 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
                 const int b = g0 + s, rows = rows_of(b), min_lanes = lanes_of(b);
                 int pick = -1;
                 for (int c = 0; c < N_CONFIGS && pick < 0; c++)
-                    if (g_configs[c].tier == tier && rows <= g_configs[c].L * g_configs[c].ET && g_configs[c].L >= min_lanes) pick = c;
+                    if (g_configs[c].tier == tier && g_configs[c].kern[dt] && rows <= g_configs[c].L * g_configs[c].ET && g_configs[c].L >= min_lanes) pick = c;
                 if (pick < 0) {
                     snprintf(g_err, sizeof g_err, "string %d: %d transverse rows are outside the built kernel set", b, rows);
                     rc = SFDTD_ERR_UNSUPPORTED; goto done;
@@ -1930,40 +2026,51 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
         std::vector<int> cls(G);
         for (int s = 0; s < G; s++) {
             const int rows = rows_of(g0 + s);
-            if (rows > 256) {
+            if (rows > (manuf ? 256 : MAX_ROWS)) {
                 snprintf(g_err, sizeof g_err, "string %d: %d transverse rows are outside the built kernel set", g0 + s, rows);
                 rc = SFDTD_ERR_UNSUPPORTED; goto done;
             }
             if (rows > 128 && kind == 0) kind = 1;
+            if (rows > 256) kind = 3;
             cls[s] = (rows > 64 || lanes_of(g0 + s) > 16) ? 1 : 0;
         }
+        // slots per CTA of the one-shape kinds: 4, or fewer (64- / 32-thread CTAs) when the longitudinal blocks of four strings
+        // do not fit one CTA's shared memory and the cluster still holds the group
         std::vector<CtaDesc> ctas;
-        for (int c = 0; c < 2; c++) {
-            const int per = (kind != 0) ? 4 : (c == 0 ? 8 : 4);
-            CtaDesc cd; memset(&cd, 0, sizeof cd);
-            cd.group = g; cd.cls = (kind != 0) ? 0 : c; cd.G = G;
-            for (int s = 0; s < G; s++) {
-                if (kind == 0 && cls[s] != c) continue;
-                if (kind != 0 && c == 1) continue;
-                cd.str[cd.n] = g0 + s; cd.gidx[cd.n] = s; cd.n++;
-                if (cd.n == per) { ctas.push_back(cd); cd.n = 0; }
+        int threads = 128;
+        size_t smem = 0;
+        int CS = 0;
+        for (int per_big = 4; per_big >= 1; per_big /= 2) {
+            ctas.clear();
+            for (int c = 0; c < 2; c++) {
+                const int per = (kind != 0) ? per_big : (c == 0 ? 8 : 4);
+                CtaDesc cd; memset(&cd, 0, sizeof cd);
+                cd.group = g; cd.cls = (kind != 0) ? 0 : c; cd.G = G;
+                for (int s = 0; s < G; s++) {
+                    if (kind == 0 && cls[s] != c) continue;
+                    if (kind != 0 && c == 1) continue;
+                    cd.str[cd.n] = g0 + s; cd.gidx[cd.n] = s; cd.n++;
+                    if (cd.n == per) { ctas.push_back(cd); cd.n = 0; }
+                }
+                if (cd.n) ctas.push_back(cd);
             }
-            if (cd.n) ctas.push_back(cd);
+            CS = (int)ctas.size();
+            threads = (kind != 0) ? 32 * per_big : 128;
+            if (CS == 1) { const GShape sh = g_gshape[kind][ctas[0].cls]; threads = std::min(threads, (ctas[0].n * sh.L + 31) / 32 * 32); }
+            smem = 0;
+            for (const CtaDesc &cd : ctas) {
+                const GShape sh = g_gshape[kind][cd.cls];
+                const int nslots = threads / sh.L;
+                size_t dbl = GB_DOUBLES + xax_doubles(a.Nx_t1, true) + (size_t)nslots * slot_fixed_doubles(sh.L, sh.ET, true, tsz) + (size_t)(nslots + 2) / 2 + 2;
+                for (int s = 0; s < nslots; s++) dbl += slot_long_doubles(long_rows(h_max[a.B + cd.str[std::min(s, cd.n - 1)]]), true, sh.L, tsz);
+                smem = std::max(smem, dbl * sizeof(double) + 16);
+            }
+            if (kind == 0 || smem <= 227 * 1024 || per_big == 1) break;
+            if ((G + per_big / 2 - 1) / (per_big / 2) > 8) break;       // the smaller CTAs would not fit one cluster
         }
-        const int CS = (int)ctas.size();
         if (CS > 8) {
             snprintf(g_err, sizeof g_err, "group %d: needs %d CTAs (a cluster holds <= 8)", g, CS);
             rc = SFDTD_ERR_UNSUPPORTED; goto done;
-        }
-        int threads = 128;
-        if (CS == 1) { const GShape sh = g_gshape[kind][ctas[0].cls]; threads = std::min(128, (ctas[0].n * sh.L + 31) / 32 * 32); }
-        size_t smem = 0;
-        for (const CtaDesc &cd : ctas) {
-            const GShape sh = g_gshape[kind][cd.cls];
-            const int nslots = threads / sh.L;
-            size_t dbl = GB_DOUBLES + xax_doubles(a.Nx_t1, true) + (size_t)nslots * slot_fixed_doubles(sh.L, sh.ET, true) + (size_t)(nslots + 2) / 2 + 2;
-            for (int s = 0; s < nslots; s++) dbl += slot_long_doubles(long_rows(h_max[a.B + cd.str[std::min(s, cd.n - 1)]]), true, sh.L);
-            smem = std::max(smem, dbl * sizeof(double) + 16);
         }
         if (smem > 227 * 1024) {
             snprintf(g_err, sizeof g_err, "group %d needs %zu bytes of shared memory per CTA (> 227 KB)", g, smem);
@@ -1997,12 +2104,12 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
             ln.need_xax = !skip_aux;
             h_ids.insert(h_ids.end(), ids.begin(), ids.end());
             // CTA size that keeps the most strings resident per SM (registers and shared memory both bound it)
-            const int regs = kernel_regs(cf.kern);
+            const int regs = kernel_regs(cf.kern[dt]);
             int best = 32; long best_res = -1;
             for (int th : {128, 96, 64, 32}) {
                 if (th % cf.L) continue;
                 if (th_force && th != std::max(th_force, cf.L)) continue;
-                const size_t b_ = smem_bytes_indep(cf, th / cf.L, a.Nx_t1, ln.WLp, ln.need_xax);
+                const size_t b_ = smem_bytes_indep(cf, th / cf.L, a.Nx_t1, ln.WLp, ln.need_xax, tsz);
                 if (b_ > 227 * 1024) continue;
                 const long by_smem = (long)((227 * 1024) / (b_ + 1024)), by_regs = 65536 / ((long)regs * th);
                 long res = std::min(std::min(by_smem, by_regs), 32L) * th;
@@ -2012,18 +2119,18 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
             ln.threads = best;
             const int per = ln.threads / cf.L;
             ln.grid = (ln.n_items + per - 1) / per;
-            ln.smem = std::max(smem_bytes_indep(cf, per, a.Nx_t1, ln.WLp, ln.need_xax), (size_t)pad_smem);
+            ln.smem = std::max(smem_bytes_indep(cf, per, a.Nx_t1, ln.WLp, ln.need_xax, tsz), (size_t)pad_smem);
             if (ln.smem > 227 * 1024) {
                 snprintf(g_err, sizeof g_err, "a bucket (L=%d, ET=%d) needs %zu bytes of shared memory (> 227 KB)", cf.L, cf.ET, ln.smem);
                 rc = SFDTD_ERR_UNSUPPORTED; goto done;
             }
-            CK(cudaFuncSetAttribute(cf.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CK(cudaFuncSetAttribute(cf.kern[dt], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             // one shared-memory carve-out for every bucket kernel, so that CTAs of different buckets can share an SM
-            CK(cudaFuncSetAttribute(cf.kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            CK(cudaFuncSetAttribute(cf.kern[dt], cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             if (use_queue) {
                 // persistent grid: what is resident at once; the warps pull their string sets from the bucket's counter
                 int per_sm = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf.kern, ln.threads, ln.smem));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf.kern[dt], ln.threads, ln.smem));
                 const int spw = 32 / cf.L, n_sets = (ln.n_items + spw - 1) / spw, wpc = ln.threads / 32;
                 const int resident = std::max(1, per_sm) * P->n_sms;
                 // tail group: the sets that would run in the last round of the resident warps, in SFDTD_QSLICES time slices
@@ -2048,11 +2155,11 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
             ln.grid = (int)kv.second.ctas.size(); ln.n_items = ln.grid / ln.cluster; ln.off = h_ctas.size(); ln.need_xax = true;
             ln.smem = std::max(kv.second.smem, (size_t)pad_smem);
             h_ctas.insert(h_ctas.end(), kv.second.ctas.begin(), kv.second.ctas.end());
-            CK(cudaFuncSetAttribute(g_group_kernels[ln.cfg], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            CK(cudaFuncSetAttribute(g_group_kernels[ln.cfg], cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            CK(cudaFuncSetAttribute(g_group_kernels[dt][ln.cfg], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CK(cudaFuncSetAttribute(g_group_kernels[dt][ln.cfg], cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             if (P->verbose)
                 fprintf(stderr, "[sfdtd] bucket grouped kind=%d cluster=%d groups=%d threads=%d grid=%d smem=%zu regs=%d\n", ln.cfg,
-                        ln.cluster, ln.n_items, ln.threads, ln.grid, ln.smem, kernel_regs(g_group_kernels[ln.cfg]));
+                        ln.cluster, ln.n_items, ln.threads, ln.grid, ln.smem, kernel_regs(g_group_kernels[dt][ln.cfg]));
             P->launches.push_back(ln);
         }
     }
@@ -2106,8 +2213,9 @@ extern "C" int sfdtd_forward_plan(sfdtd_plan *P, const sfdtd_args *args, void *c
     if (!P) { snprintf(g_err, sizeof g_err, "plan is NULL"); return SFDTD_ERR_ARG; }
     { const int v = validate(args); if (v != SFDTD_OK) return v; }
     const sfdtd_args &a = *args;
-    if (a.B != P->B || a.group_size != P->group_size || a.Nt != P->Nt || a.Nx_t1 != P->Nx_t1 || a.Nx_l1 != P->Nx_l1 || a.flags != P->flags) {
-        snprintf(g_err, sizeof g_err, "args do not match the plan (B, group_size, Nt, Nx_t1, Nx_l1, flags)");
+    if (a.B != P->B || a.group_size != P->group_size || a.Nt != P->Nt || a.Nx_t1 != P->Nx_t1 || a.Nx_l1 != P->Nx_l1 || a.flags != P->flags ||
+        a.dtype != P->dtype) {
+        snprintf(g_err, sizeof g_err, "args do not match the plan (B, group_size, Nt, Nx_t1, Nx_l1, flags, dtype)");
         return SFDTD_ERR_ARG;
     }
     if (a.Nt <= 2) return SFDTD_OK;
@@ -2116,6 +2224,7 @@ extern "C" int sfdtd_forward_plan(sfdtd_plan *P, const sfdtd_args *args, void *c
     DeviceGuard guard;
     KArgs K;
     fill_kargs(K, a);
+    const int dt = a.dtype == SFDTD_F32 ? 1 : 0;
     std::vector<cudaEvent_t> t0, t1;
     {
     CK(guard.enter(a.state_u.ptr));
@@ -2145,7 +2254,7 @@ extern "C" int sfdtd_forward_plan(sfdtd_plan *P, const sfdtd_args *args, void *c
                 K.queue = P->d_queue + ln.q_idx; K.done = P->d_queue + P->n_buckets + ln.done_off;
                 K.q_slice = ln.q_slice; K.q_nslices = ln.q_nslices; K.q_full = ln.q_full;
             }
-            g_configs[ln.cfg].kern<<<(unsigned)ln.grid, ln.threads, ln.smem, s>>>(K);
+            g_configs[ln.cfg].kern[dt]<<<(unsigned)ln.grid, ln.threads, ln.smem, s>>>(K);
         } else {
             K.ctas = P->d_ctas + ln.off;
             cudaLaunchConfig_t lc; memset(&lc, 0, sizeof lc);
@@ -2154,7 +2263,7 @@ extern "C" int sfdtd_forward_plan(sfdtd_plan *P, const sfdtd_args *args, void *c
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = (unsigned)ln.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             lc.attrs = at; lc.numAttrs = 1;
-            CK(cudaLaunchKernelEx(&lc, g_group_kernels[ln.cfg], K));
+            CK(cudaLaunchKernelEx(&lc, g_group_kernels[dt][ln.cfg], K));
         }
         g_launches++;
         CK(cudaGetLastError());
@@ -2216,24 +2325,40 @@ done:
     return rc;
 }
 
-extern "C" int sfdtd_postprocess(const sfdtd_array *uout, const sfdtd_array *zout, int32_t B, int32_t n0, int32_t n_samples,
-                                 double silence_db, int32_t normalize, int32_t bits, int64_t pcm_pitch, uint8_t *is_nan,
-                                 uint8_t *is_silent, double *gain, void *pcm_u, void *pcm_z, void *pcm_w, void *cuda_stream) {
+namespace {
+int postprocess_impl(int dtype, const sfdtd_array *uout, const sfdtd_array *zout, int32_t B, int32_t n0, int32_t n_samples,
+                     double silence_db, int32_t normalize, int32_t bits, int64_t pcm_pitch, uint8_t *is_nan,
+                     uint8_t *is_silent, double *gain, void *pcm_u, void *pcm_z, void *pcm_w, void *cuda_stream) {
     g_err[0] = 0;
     if (!uout || !zout || !uout->ptr || !zout->ptr || B <= 0 || n_samples <= 0 || n0 < 0 || (bits != 16 && bits != 24)) {
         snprintf(g_err, sizeof g_err, "bad arguments"); return SFDTD_ERR_ARG;
     }
     int rc = SFDTD_OK;
     DeviceGuard guard;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    uint8_t *pu = (uint8_t *)pcm_u, *pz = (uint8_t *)pcm_z, *pw = (uint8_t *)pcm_w;
     CK(guard.enter(uout->ptr));
-    if (bits == 16)
-        sfdtd_postprocess_kernel<16><<<B, 256, 0, (cudaStream_t)cuda_stream>>>(*uout, *zout, n0, n_samples, silence_db, normalize, is_nan,
-                                                                              is_silent, gain, (uint8_t *)pcm_u, (uint8_t *)pcm_z, (uint8_t *)pcm_w, pcm_pitch);
-    else
-        sfdtd_postprocess_kernel<24><<<B, 256, 0, (cudaStream_t)cuda_stream>>>(*uout, *zout, n0, n_samples, silence_db, normalize, is_nan,
-                                                                              is_silent, gain, (uint8_t *)pcm_u, (uint8_t *)pcm_z, (uint8_t *)pcm_w, pcm_pitch);
+#define PP_LAUNCH(BITS_, T_) sfdtd_postprocess_kernel<BITS_, T_><<<B, 256, 0, st>>>(*uout, *zout, n0, n_samples, silence_db, normalize, \
+                                                                                    is_nan, is_silent, gain, pu, pz, pw, pcm_pitch)
+    if (dtype == SFDTD_F32) { if (bits == 16) PP_LAUNCH(16, float); else PP_LAUNCH(24, float); }
+    else { if (bits == 16) PP_LAUNCH(16, double); else PP_LAUNCH(24, double); }
+#undef PP_LAUNCH
     g_launches++;
     CK(cudaGetLastError());
 done:
     return rc;
+}
+}  // namespace
+
+extern "C" int sfdtd_postprocess(const sfdtd_array *uout, const sfdtd_array *zout, int32_t B, int32_t n0, int32_t n_samples,
+                                 double silence_db, int32_t normalize, int32_t bits, int64_t pcm_pitch, uint8_t *is_nan,
+                                 uint8_t *is_silent, double *gain, void *pcm_u, void *pcm_z, void *pcm_w, void *cuda_stream) {
+    return postprocess_impl(SFDTD_F64, uout, zout, B, n0, n_samples, silence_db, normalize, bits, pcm_pitch, is_nan, is_silent, gain,
+                            pcm_u, pcm_z, pcm_w, cuda_stream);
+}
+extern "C" int sfdtd_postprocess_f32(const sfdtd_array *uout, const sfdtd_array *zout, int32_t B, int32_t n0, int32_t n_samples,
+                                     double silence_db, int32_t normalize, int32_t bits, int64_t pcm_pitch, uint8_t *is_nan,
+                                     uint8_t *is_silent, double *gain, void *pcm_u, void *pcm_z, void *pcm_w, void *cuda_stream) {
+    return postprocess_impl(SFDTD_F32, uout, zout, B, n0, n_samples, silence_db, normalize, bits, pcm_pitch, is_nan, is_silent, gain,
+                            pcm_u, pcm_z, pcm_w, cuda_stream);
 }

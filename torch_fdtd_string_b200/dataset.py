@@ -159,12 +159,13 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
         p_host = sampler.concat([q for _, q in group])
         p = sampler.to_device(p_host, device)
         Nt = p_host["Nt"]
-        f64 = dict(dtype=torch.float64, device=device)
+        # `precision: single` (the reference's default preset) runs the fp32 kernels: states, u_H and outputs float32
+        f64 = dict(dtype=torch.float32 if precision == "single" else torch.float64, device=device)
         if full_layout:
             su = torch.zeros(B, Nt, p_host["Nx_t1"], **f64); su[:, :2] = p["state_u"]
             sz = torch.zeros(B, Nt, p_host["Nx_l1"], **f64); sz[:, :2] = p["state_z"]
         else:
-            su, sz = p["state_u"].clone(), p["state_z"].clone()
+            su, sz = p["state_u"].to(f64["dtype"], copy=True), p["state_z"].to(f64["dtype"], copy=True)
         # hammer displacement: pre-loaded like the reference's Hammer module (simulator.py:573-578) and updated IN PLACE by the
         # stepper (string.cpp:303) -- the reference saves the updated tensor as hammer_params.npz:u_H
         uH = torch.zeros(B, Nt, **f64)

@@ -93,13 +93,19 @@ def build_args(state_u, state_z, *, kappa, alpha, pos, T60, phi_0, phi_1, x_H, w
     itself.  ``aux_outputs=False`` leaves v_r / F_H / u_H_out unallocated (audio only)."""
     dev = state_u.device
     assert dev.type == "cuda", "the stepper runs on CUDA only"
+    # the arithmetic type of the call is the dtype of the state: float64 (SFDTD_F64, parity mode) or float32 (SFDTD_F32,
+    # the reference's `precision: single`); states, u_H and the (B,Nt) outputs are of that type, parameters are float64
+    sdt = state_u.dtype
+    assert sdt in (torch.float64, torch.float32), sdt
     for t in (state_u, state_z):
-        assert t.dtype == torch.float64 and t.stride(-1) == 1
+        assert t.dtype == sdt and t.stride(-1) == 1
     B, Nx_t1, Nx_l1 = state_u.size(0), state_u.size(2), state_z.size(2)
     f64 = dict(dtype=torch.float64, device=dev)
     names = ("uout", "zout", "v_r", "F_H", "u_H_out") if aux_outputs else ("uout", "zout")
     if out is None:
-        out = {n: torch.zeros(B, Nt, **f64) for n in names}
+        out = {n: torch.zeros(B, Nt, dtype=sdt, device=dev) for n in names}
+    for n in names:
+        assert out[n].dtype == sdt, (n, out[n].dtype, sdt)
     sig0 = torch.zeros(B, **f64); sig1 = torch.zeros(B, **f64)
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     cnt = torch.zeros(B, 4, dtype=torch.int64, device=dev) if counters else None
@@ -113,7 +119,7 @@ def build_args(state_u, state_z, *, kappa, alpha, pos, T60, phi_0, phi_1, x_H, w
 
     a = Args()
     a.abi_version = _lib.SFDTD_ABI_VERSION
-    a.dtype = _lib.SFDTD_F64
+    a.dtype = _lib.SFDTD_F64 if sdt == torch.float64 else _lib.SFDTD_F32
     a.flags = ((_lib.SURFACE_INTEGRAL if surface_integral else 0) | (_lib.SAVE_STATE if save_state else 0)
                | (_lib.SKIP_AUX if skip_aux else 0) | (_lib.MANUFACTURED if manufactured else 0))
     a.B, a.group_size, a.Nt, a.Nx_t1, a.Nx_l1 = B, int(group_size), int(Nt), Nx_t1, Nx_l1
@@ -132,7 +138,7 @@ def build_args(state_u, state_z, *, kappa, alpha, pos, T60, phi_0, phi_1, x_H, w
         y = _synth_struct(synth, B, dev, keep)
         a.synth = ctypes.addressof(y)
     if u_H is not None:
-        assert u_H.shape == (B, Nt) and u_H.dtype == torch.float64
+        assert u_H.shape == (B, Nt) and u_H.dtype == sdt
         a.u_H = _arr(u_H, 0, 1)
     else:
         assert synth is not None, "u_H may only be omitted with synthesised controls"
@@ -158,7 +164,8 @@ def _check_status(status):
 
 
 def step_strings(state_u, state_z, *, stream=None, check=True, **kw):
-    """Native API.  All tensors are float64 CUDA tensors (see ``build_args`` for the arguments).
+    """Native API.  CUDA tensors: states, u_H and outputs float64 or float32 (the call's arithmetic type), parameters and
+    control curves float64 (see ``build_args`` for the arguments).
 
     state_u/state_z: (B, Nt, Nx) when ``save_state`` (reference layout, updated in place), else
     (B, 2, Nx) holding rows [n-2, n-1] (overwritten with the last two rows).  Control curves
@@ -230,7 +237,7 @@ def synth_controls(synth, B, Nt, device, k=None):
 def postprocess(uout, zout, n0=2, n_samples=None, silence_db=-23.0, normalize=True, bits=24, pcm=("u", "z", "w"), stream=None,
                 out=None):
     """Device-side NaN / silence flags, l-infinity gain and PCM quantisation of the audio (sfdtd_postprocess; reference
-    src/task/simulate.py:333-337,416-425, src/utils/audio.py:42-48,72-76).  uout, zout: (B,Nt) float64 CUDA tensors.
+    src/task/simulate.py:333-337,416-425, src/utils/audio.py:42-48,72-76).  uout, zout: (B,Nt) float64 or float32 CUDA tensors.
     Returns dict(is_nan, is_silent (B) uint8, gain (B), pcm_u / pcm_z / pcm_w (B, pitch) uint8 rows of packed little-endian
     PCM_16 / PCM_24 samples, pitch = row bytes rounded up to 16)."""
     lib = _lib.load()
@@ -252,7 +259,9 @@ def postprocess(uout, zout, n0=2, n_samples=None, silence_db=-23.0, normalize=Tr
     ua, za = _arr(uout, 0, 1), _arr(zout, 0, 1)
     s = torch.cuda.current_stream() if stream is None else stream
     with torch.cuda.device(dev):
-        rc = lib.sfdtd_postprocess(ctypes.byref(ua), ctypes.byref(za), B, int(n0), n_samples, float(silence_db),
+        assert uout.dtype == zout.dtype and uout.dtype in (torch.float64, torch.float32)
+        fn = lib.sfdtd_postprocess if uout.dtype == torch.float64 else lib.sfdtd_postprocess_f32
+        rc = fn(ctypes.byref(ua), ctypes.byref(za), B, int(n0), n_samples, float(silence_db),
                                    1 if normalize else 0, int(bits), pitch, res["is_nan"].data_ptr(), res["is_silent"].data_ptr(),
                                    res["gain"].data_ptr(), ptr["u"], ptr["z"], ptr["w"], ctypes.c_void_p(s.cuda_stream))
     if rc != 0:
@@ -295,9 +304,11 @@ def forward_fn(state_u, state_z, string_params, bow_params, hammer_params,
     Same positional arguments; returns ``[uout, zout, state_u, state_z, v_r, F_H, u_H/k, sig0, sig1]``
     and, like the reference, updates ``state_u``, ``state_z`` and ``hammer_params[2]`` in place.
     All strings of the call form one group (the reference's batch).  Tensors may live on the CPU
-    or on CUDA and be float32 or float64: the arithmetic is float64 on the GPU either way (float32
-    tensors are widened on entry and rounded on exit), results are returned on CUDA like the
-    reference's ``device()`` (misc.cpp:13-15) does when a GPU is visible.
+    or on CUDA.  float64 tensors run the fp64 kernels (parity mode); float32 tensors (the reference's
+    ``precision: single``) run the fp32 kernels -- grid sizes from the reference's float32 evaluation of
+    ``get_derived_vars``, states / solves / outputs in float32 -- unless ``SFDTD_WIDEN_F32=1``, which widens
+    them to float64 on entry and rounds on exit.  Results are returned on CUDA like the reference's
+    ``device()`` (misc.cpp:13-15) does when a GPU is visible.
     """
     if not torch.cuda.is_available():
         raise RuntimeError("torch_fdtd_string_b200.forward_fn needs a CUDA device (no CPU fallback)")
@@ -308,17 +319,21 @@ def forward_fn(state_u, state_z, string_params, bow_params, hammer_params,
     B, Nt_c, _ = state_u.shape
     assert Nt == Nt_c, (Nt, Nt_c)
 
+    import os
+    sdt = torch.float32 if (state_u.dtype == torch.float32 and os.environ.get("SFDTD_WIDEN_F32", "0") != "1"
+                            and not manufactured) else torch.float64
+
     def D(t):   # float64 on the device; aliases the input when it already is
         return t.detach().to(device=dev, dtype=torch.float64)
 
     def Dio(t):  # in/out tensor: (device copy with unit space stride, needs_copy_back)
-        d = D(t)
+        d = t.detach().to(device=dev, dtype=sdt)
         if d.stride(-1) != 1:
             d = d.contiguous()
         return d, d.data_ptr() != t.data_ptr()
 
     su, su_cp = Dio(state_u); sz, sz_cp = Dio(state_z)
-    uH = D(u_H)
+    uH = u_H.detach().to(device=dev, dtype=sdt)
     if uH.dim() != 2 or uH.shape != (B, Nt):
         uH = uH.expand(B, Nt).contiguous()
     uH_cp = uH.data_ptr() != u_H.data_ptr()

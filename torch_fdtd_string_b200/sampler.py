@@ -263,12 +263,15 @@ def synth_dict(p):
 
 
 def compact_args(p_dev, group_size, surface_integral=True, skip_aux=False, counters=False, out=None, n_run=None,
-                 aux_outputs=True, su=None, sz=None):
-    """(args, results, keep) of a synthesised-control call for compact device parameters (see forward_fn.build_args)"""
+                 aux_outputs=True, su=None, sz=None, precision="double"):
+    """(args, results, keep) of a synthesised-control call for compact device parameters (see forward_fn.build_args);
+    precision "single" runs the fp32 kernels (states and outputs float32)"""
     from .forward_fn import build_args
+    import torch as _t
     n_run = p_dev["Nt"] if n_run is None else int(n_run)
-    su = p_dev["state_u"].clone() if su is None else su
-    sz = p_dev["state_z"].clone() if sz is None else sz
+    sdt = _t.float32 if precision == "single" else _t.float64
+    su = p_dev["state_u"].to(sdt, copy=True) if su is None else su
+    sz = p_dev["state_z"].to(sdt, copy=True) if sz is None else sz
     return build_args(
         su, sz, kappa=p_dev["kappa"], alpha=p_dev["alpha"], pos=p_dev["pos"], T60=p_dev["T60"],
         phi_0=p_dev["phi_0"], phi_1=p_dev["phi_1"], x_H=p_dev["x_H"], w_H=p_dev["w_H"], M_r=p_dev["M_r"],
@@ -279,7 +282,7 @@ def compact_args(p_dev, group_size, surface_integral=True, skip_aux=False, count
 
 
 def run_compact(p_dev, group_size, surface_integral=True, skip_aux=False, counters=False, controls=None, out=None,
-                n_run=None, synth=True, aux_outputs=True):
+                n_run=None, synth=True, aux_outputs=True, precision="double"):
     """compact device params -> audio for the first `n_run` samples (default: the full length).  ``synth`` (default): the
     stepper synthesises the control curves itself; otherwise they are expanded to (B,n_run) arrays first (``controls`` may
     pass them in)."""
@@ -288,17 +291,19 @@ def run_compact(p_dev, group_size, surface_integral=True, skip_aux=False, counte
     dev = p_dev["kappa"].device
     n_run = p_dev["Nt"] if n_run is None else int(n_run)
     if synth and controls is None:
-        a, res, keep = compact_args(p_dev, group_size, surface_integral, skip_aux, counters, out, n_run, aux_outputs)
+        a, res, keep = compact_args(p_dev, group_size, surface_integral, skip_aux, counters, out, n_run, aux_outputs,
+                                    precision=precision)
         with _t.cuda.device(dev):
             _call(a)
         res["_keep"] = keep
         return res
     c = controls if controls is not None else expand_controls(p_dev, dev, n_run)
-    su = p_dev["state_u"].clone(); sz = p_dev["state_z"].clone()
+    sdt = _t.float32 if precision == "single" else _t.float64
+    su = p_dev["state_u"].to(sdt, copy=True); sz = p_dev["state_z"].to(sdt, copy=True)
     res = step_strings(
         su, sz, kappa=p_dev["kappa"], alpha=p_dev["alpha"], f0=c["f0"], pos=p_dev["pos"], T60=p_dev["T60"],
         x_b=c["x_b"], v_b=c["v_b"], F_b=c["F_b"], wid=c["wid"], phi_0=p_dev["phi_0"], phi_1=p_dev["phi_1"],
-        x_H=p_dev["x_H"], w_H=p_dev["w_H"], M_r=p_dev["M_r"], alpha_H=p_dev["alpha_H"], u_H=c["u_H"].clone(),
+        x_H=p_dev["x_H"], w_H=p_dev["w_H"], M_r=p_dev["M_r"], alpha_H=p_dev["alpha_H"], u_H=c["u_H"].to(sdt, copy=True),
         bow_mask=p_dev["bow_mask"], hammer_mask=p_dev["hammer_mask"], k=p_dev["k"], theta_t=p_dev["theta_t"],
         lambda_c=p_dev["lambda_c"], relative_order=p_dev["relative_order"], Nt=n_run, group_size=group_size,
         surface_integral=surface_integral, save_state=False, skip_aux=skip_aux, p_a=p_dev["p_a"], counters=counters, out=out,
