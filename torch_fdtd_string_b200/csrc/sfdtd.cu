@@ -77,6 +77,9 @@ constexpr int NLA_G = 6;            // grouped mode: + ZP (previous fixed-point 
 // over 8); grouped mode: 8, its CTAs are at the shared-memory limit.
 constexpr int TBS_I = 16, TBS_G = 8;
 constexpr int TBS_MAX = TBS_I > TBS_G ? TBS_I : TBS_G;
+#ifndef SFDTD_F32_TOL
+#define SFDTD_F32_TOL 1e-7f     // fp32 build: predicted relative error that ends the sweeps
+#endif
 #ifndef SFDTD_PREDICT_SWEEPS
 #define SFDTD_PREDICT_SWEEPS 1
 #endif
@@ -427,7 +430,7 @@ template <> struct Real<double> {
 template <> struct Real<float> {
     // float32 round-off of one solve is ~2e-7 of the solution's max-norm: the sweeps run down to it (the reference's direct
     // float32 solve is that accurate, and per-step errors accumulate linearly over the run)
-    static constexpr float GS_TOL = 1e-7f;
+    static constexpr float GS_TOL = SFDTD_F32_TOL;
     static constexpr float E_FLOOR = 4e-7f;
     static constexpr float RATE_MIN = 2e-5f;
 };
@@ -1611,8 +1614,12 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 #ifndef SFDTD_GROUP_MINB
 #define SFDTD_GROUP_MINB 3
 #endif
+#ifndef SFDTD_F32_GROUP_MINB
+#define SFDTD_F32_GROUP_MINB 3
+#endif
 template <typename T, int KIND>
-__global__ void __launch_bounds__(128, KIND == 0 ? SFDTD_GROUP_MINB : 1) sfdtd_group_kernel(const __grid_constant__ KArgs A) {
+__global__ void __launch_bounds__(128, KIND == 0 ? (sizeof(T) == 4 ? SFDTD_F32_GROUP_MINB : SFDTD_GROUP_MINB) : 1)
+sfdtd_group_kernel(const __grid_constant__ KArgs A) {
     const CtaDesc *cd = A.ctas + blockIdx.x;
     if (KIND == 0) {
         if (cd->cls == 0) step_body<T, 16, 4, true, false>(A, cd);
@@ -1726,8 +1733,14 @@ __global__ void __launch_bounds__(256) sfdtd_fma_peak_kernel(T *out, int iters, 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 
+#ifndef SFDTD_F32_L8
+#define SFDTD_F32_L8 0
+#endif
+#ifndef SFDTD_F32_L8_MINB
+#define SFDTD_F32_L8_MINB 3
+#endif
 #ifndef SFDTD_F32_MINB
-#define SFDTD_F32_MINB 5            // CTAs per SM the small fp32 kernels are compiled for (register cap 65536 / (128 x MINB))
+#define SFDTD_F32_MINB 4            // CTAs per SM the small fp32 kernels are compiled for (register cap 65536 / (128 x MINB))
 #endif
 // independent-mode kernels: <=128-thread CTAs, a string needs rows <= L*ET; tier = kernel set
 // (tier 2, the default: 16 lanes x 4 rows for every string up to 64 rows, then 32x4, 32x8 -- measured fastest; tier 0 also
@@ -1737,8 +1750,14 @@ std::atomic<int64_t> g_launches{0};
 struct Config { int L, ET, tier; void (*kern[2])(const KArgs); };
 #define CFG_I(L_, ET_, MB_, TIER_) Config{L_, ET_, TIER_, {sfdtd_step_kernel<double, L_, ET_, 128, MB_>, nullptr}}
 #define CFG_D(L_, ET_, MB_, MB32_, TIER_) Config{L_, ET_, TIER_, {sfdtd_step_kernel<double, L_, ET_, 128, MB_>, sfdtd_step_kernel<float, L_, ET_, 128, MB32_>}}
+#define CFG_F(L_, ET_, MB32_, TIER_) Config{L_, ET_, TIER_, {nullptr, sfdtd_step_kernel<float, L_, ET_, 128, MB32_>}}
 const Config g_configs[] = {   // smallest first
     CFG_I(8, 4, 3, 0), CFG_I(8, 6, 2, 0), CFG_I(16, 4, 3, 0), CFG_I(16, 6, 2, 0), CFG_I(32, 4, 3, 0), CFG_I(32, 8, 1, 0),
+#if SFDTD_F32_L8
+    // fp32 only: 8 lanes x 8 rows (a float row costs half the registers of a double one: twice the rows per lane, one
+    // cyclic-reduction level and half the shuffles per row less)
+    CFG_F(8, 8, SFDTD_F32_L8_MINB, 2),
+#endif
     CFG_D(16, 4, 3, SFDTD_F32_MINB, 2), CFG_D(32, 4, 3, SFDTD_F32_MINB, 2), CFG_D(32, 8, 1, 2, 2), CFG_D(32, 12, 1, 1, 2), CFG_D(32, 20, 1, 1, 2),
     CFG_I(8, 4, 3, 3), CFG_I(16, 4, 3, 3), CFG_I(32, 4, 3, 3), CFG_I(32, 8, 1, 3),
 };
