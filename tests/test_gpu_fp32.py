@@ -49,7 +49,8 @@ def test_fp32_kernels_within_the_references_own_fp32_distance(name):
             continue
         mine = gu.rel_l2(x, g[k])                      # fp32 kernels vs the fp64 reference
         ref = gu.rel_l2(r32[k], g[k])                  # the reference's float32 run vs its fp64 run
-        line.append(f"{k} {mine:.1e} (ref32 {ref:.1e})")
+        both = gu.rel_l2(x, r32[k].astype(np.float64))     # fp32 kernels vs the reference's float32 run
+        line.append(f"{k} {mine:.1e} (ref32 {ref:.1e}; to ref32 {both:.1e})")
         # (the auxiliary outputs of strings that are not bowed / hammered amplify the state's round-off through the contact
         # nonlinearity: twice the margin)
         assert mine <= (MARGIN if k in ("uout", "zout") else 2 * MARGIN) * max(ref, FLOOR), (name, k, mine, ref)
