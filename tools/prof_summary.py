@@ -26,6 +26,7 @@ summary = {
     "warp_instructions": int(f("smsp__inst_executed.sum")), "warp_instructions_per_string_step": f("smsp__inst_executed.sum") / ss,
     "issue_slots_busy_pct": f("sm__inst_issued.avg.pct_of_peak_sustained_active"),
     "fp64_pipe_pct": f("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+    "fma_pipe_pct": (f("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active") if "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active" in d else None),
     "lsu_pipe_pct": f("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
     "alu_pipe_pct": f("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
     "smem_wavefronts_per_string_step": f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum") / ss,
@@ -40,11 +41,13 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, capture_output=True)
 cubin = [x for x in os.listdir(tmp) if x.endswith(".cubin")][0]
 li = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+ty = {"double": "d", "float": "f"}
 if "group_kernel" in d["Kernel Name"]:
-    mangled = "sfdtd_group_kernelILi" + re.search(r"group_kernel<\(?(?:int\))?(\d)>", d["Kernel Name"]).group(1) + "E"
+    m = re.search(r"group_kernel<(double|float), \(?(?:int\))?(\d)>", d["Kernel Name"])
+    mangled = "sfdtd_group_kernelI" + ty[m.group(1)] + "Li" + m.group(2) + "E"
 else:
-    kn = re.search(r"<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d)>", d["Kernel Name"]).groups()
-    mangled = f"sfdtd_step_kernelILi{kn[0]}ELi{kn[1]}ELi{kn[2]}ELi{kn[3]}EEE"
+    kn = re.search(r"<(double|float), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d)>", d["Kernel Name"]).groups()
+    mangled = f"sfdtd_step_kernelI{ty[kn[0]]}Li{kn[1]}ELi{kn[2]}ELi{kn[3]}ELi{kn[4]}EEE"
 start = [i for i, l in enumerate(li) if l.startswith(".text.") and mangled in l][0]
 end = next(i for i in range(start + 1, len(li)) if li[i].startswith("//-----"))
 cur, lines = None, []

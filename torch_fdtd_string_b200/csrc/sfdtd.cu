@@ -569,9 +569,10 @@ template <int L, int ET, typename T> __device__ __forceinline__ T fetch_row(cons
 // Two 8-lane strings share a 16-lane shared-memory wavefront: their slots are spaced by 8 (mod 16) doubles, which puts the
 // blocked row accesses (lane stride ET+1 doubles, ET = 4 or 6) and the consecutive longitudinal accesses of the two strings
 // into disjoint banks.
-__host__ __device__ inline int slot_spacing(int n, int L) {
+// (fp32 build: the same holds for two 16-lane strings of 4-byte rows sharing a 32-lane wavefront)
+__host__ __device__ inline int slot_spacing(int n, int L, int tsz = 8) {
     n = (n + 1) & ~1;                 // 16-byte aligned slots (int4 / double2 loads)
-    if (L <= 8) n += (24 - (n & 15)) & 15;      // == 8 (mod 16)
+    if (L <= 8 || (tsz == 4 && L <= 16)) n += (24 - (n & 15)) & 15;      // == 8 (mod 16)
     else if ((n & 15) == 0) n += 2;   // one string per half-warp: the slots only should not start in the same bank
     return n;
 }
@@ -581,11 +582,11 @@ __host__ __device__ inline int slot_fixed_doubles(int L, int ET, bool grouped, i
     const int TBS = grouped ? TBS_G : TBS_I;
     const int rows = (LE + L + 2) + 2 * (LE + L + 6) + (grouped ? LE + L : 0);
     const int n = TBS * (grouped ? NV_G : NV_I) + TBS * NI / 2 + TBS * NOUT + NCONST + (rows * tsz + 7) / 8;
-    return slot_spacing(n, L);
+    return slot_spacing(n, L, tsz);
 }
 __host__ __device__ inline int slot_long_doubles(int W, bool grouped, int L, int tsz) {
     const int n = ((((grouped ? NLA_G : NLA_I) * W + 2 * W) * tsz + 7) / 8 + (W + 1) / 2 + 1) & ~1;
-    return L <= 8 ? slot_spacing(n, L) : n;
+    return (L <= 8 || (tsz == 4 && L <= 16)) ? slot_spacing(n, L, tsz) : n;
 }
 __host__ __device__ inline int long_rows(int maxNl) { return (maxNl + 1 + WL_MARGIN + 2 + 1) & ~1; }   // + 2 guards, even
 
