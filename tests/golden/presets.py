@@ -61,9 +61,9 @@ LINEAR12 = dict(LINEAR, sr=12000); LINEAR24 = dict(LINEAR, sr=24000); LINEAR96 =
 
 # the reference's own default ranges reach f0_min = 27.5 Hz and kappa_min = 0 (src/model/simulator.py:123): N_t up to ~556 rows
 # at 48 kHz (the stiffness term shortens the grid: kappa_rel = 0.03 gives N_t ~ 100 at 25 Hz, so kappa is kept small here)
-LOWF0 = dict(NSYNTH, theta=("auto", 0.001, 25.0), f0_inf=25.0, alpha_inf=8,
+LOWF0 = dict(NSYNTH, theta=("auto", 0.001, 25.0), f0_inf=25.0, alpha_inf=1.5,
              string_kwargs=dict(NSYNTH['string_kwargs'], f0_min=27.5, f0_max=36.0, f0_diff_max=3, kappa_min=0.0002, kappa_max=0.002,
-                                alpha_min=8., alpha_max=25.))
+                                alpha_min=1.5, alpha_max=3., p_a_max=0.004))
 
 PRESETS = dict(nsynth=NSYNTH, lowf0=LOWF0, allfixed=ALLFIXED, linear=LINEAR, finehammer=FINEHAMMER, finehammer192=FINEHAMMER192,
                linear12=LINEAR12, linear24=LINEAR24, linear96=LINEAR96)

@@ -3,7 +3,7 @@
 
 Stated bound (BASELINE.json north_star: "a stated bound for an fp32 mode"): on every fixture and output the fp32 kernels are
 within 4 x the distance the reference's OWN float32 run of the same inputs keeps from its fp64 run (relative L2 over the
-fixture; floor 2e-5), and within 1e-3 on uout.  Float32 round-off is a random walk over the steps, so two float32
+fixture; floor 2e-5), and per string within 1e-3 on uout wherever the reference's own float32 run is within 2.5e-4.  Float32 round-off is a random walk over the steps, so two float32
 implementations land at comparable, not identical, distances: measured on B200 the kernels are between 17 x closer
 (pluck_b1 uout 1.6e-5 vs the reference's 2.8e-4) and 2.7 x further (pluck_b3_pickup 1.7e-4 vs 5.5e-5) than the reference's
 float32 run.  Those runs are committed as tests/golden/f32/<name>.npz (tests/golden/make_golden.py --single: the fixture's
@@ -55,7 +55,16 @@ def test_fp32_kernels_within_the_references_own_fp32_distance(name):
         # nonlinearity: twice the margin)
         assert mine <= (MARGIN if k in ("uout", "zout") else 2 * MARGIN) * max(ref, FLOOR), (name, k, mine, ref)
         if k == "uout":
-            assert mine <= 1e-3, (name, mine)
+            # per string: <= 1e-3 wherever the reference's own float32 run stays within 2.5e-4 of its fp64 run (the string of
+            # `pluck_b24` that amplifies 1-ulp perturbations in fp64 -- DESIGN.md "Sensitivity" -- is 5e-2 away after 4 ms in the
+            # reference's float32 run and 4.5e-2 here: float32 round-off is 1e8 ulp of a double)
+            for b in range(x.shape[0]):
+                mb, rb = gu.rel_l2(x[b], g[k][b]), gu.rel_l2(r32[k][b], g[k][b])
+                if rb > 2.5e-4 or mb > 2.5e-4:
+                    print(f"  {name} uout[{b}]: kernels {mb:.1e}, reference float32 {rb:.1e}, kernels to reference float32 "
+                          f"{gu.rel_l2(x[b], r32[k][b].astype(np.float64)):.1e}")
+                if rb <= 2.5e-4:
+                    assert mb <= 1e-3, (name, b, mb, rb)
     print(name, "; ".join(line))
     # in-place side effects land in the caller's float32 tensors (string.cpp:264-265, 303)
     assert out["state_u"].data_ptr() == inp["state_u"].data_ptr() and inp["state_u"].dtype == torch.float32
@@ -105,3 +114,19 @@ def test_fp32_hammer_bow_groups():
         outer = float(r32["counters"][:, 0].sum()) / float(r32["counters"][:, 3].sum())
         print(ex, "fp32 vs fp64: median %.1e q90 %.1e; outer iterations/step %.2f" % (float(q[0]), float(q[1]), outer))
         assert float(q[0]) < 1e-3 and 1.5 < outer < 4.0, (ex, float(q[0]), outer)
+
+
+def test_fp32_dataset_files(tmp_path):
+    """`task.precision: single`: the dataset driver runs the fp32 kernels and writes what the reference writes in that mode --
+    PCM_16 wavs (src/task/simulate.py:416-425) and float32 archives."""
+    import wave
+    from torch_fdtd_string_b200 import dataset
+    st = dataset.generate(str(tmp_path), num_samples=24, batch_size=24, excitation="pluck", length=0.05, seed=5, precision="single")
+    assert st["strings"] == 24 and st["written"] > 12
+    d = tmp_path / sorted(os.listdir(tmp_path))[0]
+    w = wave.open(str(d / "output-u.wav"))
+    assert (w.getframerate(), w.getnframes(), w.getsampwidth()) == (48000, 2400 - 2, 2)
+    v = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16).astype(np.int64)
+    assert abs(np.abs(v).max() - 32767) <= 1                                   # l-infinity normalised
+    sim = np.load(d / "simulation.npz")
+    assert sim["uout"].dtype == np.float32 and sim["uout"].shape == (2398,) and np.isfinite(sim["uout"]).all()

@@ -28,7 +28,7 @@ def test_oracle_on_low_f0_fixtures(oracle, name):
     """Strings of more than 256 transverse rows (f0 down to the reference's default floor): the dense LU of ~1000 unknowns
     per pass limits the oracle to a prefix here; the CUDA path is compared at the fixture's length on the GPU."""
     g = gu.load_golden(name)
-    n = 10
+    n = 6
     out = gu.run_process(oracle.forward_fn, _cut(g, gu.build_inputs(g), n))
     for k in KEYS:
         assert gu.rel_l2(out[k].numpy(), g[k][:, :n - 2]) < 1e-10, (name, k)
