@@ -22,7 +22,7 @@ def lib():
 def declared_functions():
     src = open(HDR).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(sfdtd_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(sfdtd_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_exports_every_declared_symbol(lib):
