@@ -55,6 +55,8 @@ CASES = dict(
     lowf0_pluck_b2=dict(preset='lowf0', model='pluck', B=2, length=0.002, seed=21, threads=1),
     lowf0_hammer_b2=dict(preset='lowf0', model='hammer', B=2, length=0.002, seed=22, threads=1),
     lowf0_bow_b2=dict(preset='lowf0', model='bow', B=2, length=0.002, seed=23, threads=1),
+    # strings that blow up: NaN mask and onset (with the perturbed twin: the reference's own onset shift)
+    pluck_hot_b6=dict(preset='hot', model='pluck', B=6, length=0.06, seed=31, long=True, threads=2, keys=('uout', 'zout')),
     # ---- full-length runs of the BASELINE configs (long format: audio outputs only, time-constant curves stored once) ----
     # configs[0]: single plucked string, nsynth-like, 1 s @ 48 kHz (reference ~8 min)
     pluck_b1_1s=dict(preset='nsynth', model='pluck', B=1, length=1.0, long=True, threads=1),

@@ -65,6 +65,11 @@ LOWF0 = dict(NSYNTH, theta=("auto", 0.001, 25.0), f0_inf=25.0, alpha_inf=1.5,
              string_kwargs=dict(NSYNTH['string_kwargs'], f0_min=27.5, f0_max=36.0, f0_diff_max=3, kappa_min=0.0002, kappa_max=0.002,
                                 alpha_min=1.5, alpha_max=3., p_a_max=0.004))
 
-PRESETS = dict(nsynth=NSYNTH, lowf0=LOWF0, allfixed=ALLFIXED, linear=LINEAR, finehammer=FINEHAMMER, finehammer192=FINEHAMMER192,
+# strings that blow up to NaN within tens of milliseconds in the reference (large alpha, large pluck amplitude, fine grid):
+# pins the NaN mask and onset (src/task/simulate.py:91-93,333-334 drops such strings)
+HOT = dict(NSYNTH, string_kwargs=dict(NSYNTH['string_kwargs'], f0_min=98.0, f0_max=140.0, alpha_min=18., alpha_max=25.,
+                                      sampling_p_a='fix', p_a_fixed=0.02, kappa_min=0.01, kappa_max=0.015))
+
+PRESETS = dict(nsynth=NSYNTH, lowf0=LOWF0, hot=HOT, allfixed=ALLFIXED, linear=LINEAR, finehammer=FINEHAMMER, finehammer192=FINEHAMMER192,
                linear12=LINEAR12, linear24=LINEAR24, linear96=LINEAR96)
 

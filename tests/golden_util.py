@@ -10,7 +10,7 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-LONG = ("pluck_b1_1s", "pluck_b24_1s", "allfixed_bow_b1_4s", "finehammer192_b1", "pluck_b24_01s")   # full-length fixtures
+LONG = ("pluck_b1_1s", "pluck_b24_1s", "allfixed_bow_b1_4s", "finehammer192_b1", "pluck_b24_01s", "pluck_hot_b6")   # full-length fixtures
 
 
 def golden_names(long=False):
