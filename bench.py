@@ -514,10 +514,20 @@ def main():
         copy_stream = torch.cuda.Stream(device=dev)
         d2h_bytes = 3 * B * pitch + 3 * B * 8
 
-        def e2e_step(i):
-            q = sampler.to_device(ph, dev, non_blocking=True)
-            a_, r_, k_ = sampler.compact_args(q, GROUP, skip_aux=a.skip_aux, out=out, aux_outputs=False)
-            pl = Plan(a_)
+        side = torch.cuda.Stream(device=dev)     # inputs + plan of the NEXT step are prepared here while the current one runs
+        main = torch.cuda.current_stream()
+
+        def prepare():
+            # host -> device copy of the step's inputs and the plan (prepass kernel, its small read-back, bucketing): on the side
+            # stream, so that the host never waits for the stepper here and the GPU never waits for the host
+            with torch.cuda.stream(side):
+                q = sampler.to_device(ph, dev, non_blocking=True)
+                a_, r_, k_ = sampler.compact_args(q, GROUP, skip_aux=a.skip_aux, out=out, aux_outputs=False)
+                pl = Plan(a_)                    # synchronises the side stream only
+            return (q, a_, r_, k_, pl)           # (kept alive by the caller until the step's kernels have completed)
+
+        def launch(i, prep):
+            q, a_, r_, k_, pl = prep
             pl.run(a_)
             pp = postprocess(out["uout"], out["zout"], n0=2, bits=24, out=pcm[i % 2])
             fl = torch.stack([pp["is_nan"].double(), pp["is_silent"].double(), pp["gain"]])
@@ -533,23 +543,38 @@ def main():
                         r1 = min(B, r0 + chunk_rows)
                         stage[j % 2][: r1 - r0].copy_(src[r0:r1], non_blocking=True)
                         j += 1
+                done = torch.cuda.Event(enable_timing=True); done.record(copy_stream)
             fl.record_stream(copy_stream)
-            return (q, a_, r_, k_)
+            arrived.append(done)
+            return ev
 
-        held = e2e_step(0)
+        arrived = []                             # per step: event after the last byte of its results reached the host buffers
+        prep = prepare()
+        ev = launch(0, prep)
         barrier()
-        t0 = time.perf_counter()
+        arrived.clear()
         # the last step's read-back is not hidden: amortised over the pipelined steps (a dataset run pipelines hundreds)
         n_e2e = max(1, min(a.steps, 12)) if a.length < 0.5 else max(6, min(a.steps, 12))
+        t0 = time.perf_counter()
+        prep = prepare()
         for i in range(n_e2e):
-            held = e2e_step(i + 1)
+            held = prep
+            ev = launch(i + 1, prep)             # stepper + post-processing of step i+1 on the main stream, read-back on the copy stream
+            if i + 1 < n_e2e:
+                prep = prepare()                 # overlaps the stepper of step i+1
+            ev.synchronize()                     # one call in flight: a launch queued behind a running call slows it down (--async-steps)
         barrier()
-        te = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        # value: wall clock of the n pipelined steps incl. the un-hidden read-back of the last one (cold-start + drain);
+        # steady state: interval between the arrival of the first and of the last step's results on the host
+        steady = arrived[0].elapsed_time(arrived[-1]) * 1e-3 / max(1, len(arrived) - 1) if len(arrived) > 1 else float("nan")
+        te = torch.tensor([(time.perf_counter() - t0) / n_e2e, steady], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": string_seconds / float(te), "unit": "string-seconds/s",
+        e2e = {"value": string_seconds / float(te[0]), "unit": "string-seconds/s",
                "h2d_bytes_per_step": world * sampler.compact_nbytes(p_host), "d2h_bytes_per_step": world * d2h_bytes,
-               "ms_per_step": float(te) * 1e3,
+               "ms_per_step": float(te[0]) * 1e3, "pipelined_steps": n_e2e,
+               "steady_state": {"value": string_seconds / float(te[1]), "ms_per_step": float(te[1]) * 1e3,
+                                "note": "interval between the host arrival of consecutive steps' results (a dataset run pipelines hundreds of steps: the drain of the last one vanishes)"},
                "note": "all ranks, every step: pinned host compact parameters -> H2D -> plan -> stepper (in-kernel control synthesis) -> "
                        "device NaN/silence/gain + PCM_24 quantisation -> D2H of output-u/-z/sum PCM (copy stream, overlapping the next step)"}
 
