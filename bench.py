@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--async-steps", action="store_true", help="diagnostics: queue all timed steps without synchronising the host in "
                     "between (measured 10-15 %% slower per step on B200: launches queued behind a running call slow it down)")
     ap.add_argument("--p-a-max", type=float, default=None, help="override the pluck amplitude cap (diagnostics only)")
+    ap.add_argument("--no-grouped", action="store_true", help="skip the short hammer / bow / random legs")
     ap.add_argument("--no-dataset", action="store_true", help="skip the result-file leg (dataset.generate to a scratch directory)")
     ap.add_argument("--dataset-strings", type=int, default=240)
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32 leg (the reference's `precision: single` preset on the fp32 kernels)")
@@ -312,6 +313,53 @@ def run_fp32(a, p, out64, dev, rank, world):
                     "its 10 ms fixtures is 4e-5 ... 3e-4 (tests/golden/f32)"}
 
 
+def run_grouped(a, dev, rank, world, peak64):
+    """Grouped mode (BASELINE configs[1] names pluck / hammer): reference batches whose strings are hammered / bowed / mixed run as
+    thread-block clusters with any-over-batch votes (string.cpp:252-253, hammer.cpp:51).  Short legs (14 208 strings x 0.05 s per
+    GPU, fp64, reference-faithful outputs) so that the driver's record carries them beside the pluck headline."""
+    import torch
+    import torch.distributed as dist
+    from torch_fdtd_string_b200 import sampler
+    from torch_fdtd_string_b200.forward_fn import Plan
+    rows = {}
+    B, length = 4 * 148 * GROUP, 0.05            # four groups per SM: a cluster of a typical batch is 4 CTAs, 3 CTAs fit an SM
+    for ex in ("hammer", "bow", "random"):
+        ph = sampler.sample_nsynth_like(B, sr=SR, length=length, excitation=ex, seed=4321 + rank)
+        p = sampler.to_device(ph, dev)
+        Nt = ph["Nt"]
+        su = p["state_u"].clone(); sz = p["state_z"].clone()
+        args, res, keep = sampler.compact_args(p, GROUP, counters=True, su=su, sz=sz)
+        plan = Plan(args)
+
+        def one_step():
+            su.copy_(p["state_u"]); sz.copy_(p["state_z"]); res["status"].zero_(); res["counters"].zero_()
+            plan.run(args)
+
+        one_step(); torch.cuda.synchronize()
+        counters = res["counters"].clone()
+        if world > 1:
+            dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            one_step()
+            torch.cuda.synchronize()
+        e1.record(); torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) * 1e-3 / 2], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        per_step = float(tt)
+        plan.close()
+        flops, flops_exec, gpu_upd, _, _ = algorithmic_work(p, counters, GROUP, Nt)
+        rows[ex] = {"value": world * B * (Nt - 2) / SR / per_step, "unit": "string-seconds/s", "ms_per_step": per_step * 1e3,
+                    "frac": flops / per_step / 1e12 / peak64, "frac_executed": flops_exec / per_step / 1e12 / peak64,
+                    "mean_outer_iters": float(counters[:, 0].sum()) / max(1.0, float(counters[:, 3].sum())),
+                    "status_bits": int(res["status"].max())}
+        del plan, args, res, keep, su, sz, p
+    rows["config"] = f"{B} strings/GPU in reference batches of {GROUP}, {length} s @ 48 kHz, fp64, frac of the FP64 FMA peak ({peak64:.1f} TFLOP/s)"
+    return rows
+
+
 def run_dataset(a, dev):
     """`python -m run experiment=nsynth-like` downstream of the stepper: reference batches -> stepper -> device NaN / silence /
     gain / PCM -> the reference's result files (three wavs, four compressed archives, one yaml per kept string;
@@ -426,7 +474,10 @@ def main():
             bow_mask=p["bow_mask"], hammer_mask=p["hammer_mask"], k=p["k"], theta_t=p["theta_t"],
             lambda_c=p["lambda_c"], relative_order=p["relative_order"], Nt=Nt, group_size=GROUP,
             surface_integral=True, save_state=False, skip_aux=a.skip_aux, p_a=p["p_a"], out=out, counters=True)
+    torch.cuda.synchronize()
+    t_plan = time.perf_counter()
     plan = Plan(args)                             # prepass + one device->host read, outside the timed region
+    t_plan = time.perf_counter() - t_plan
 
     def one_step():
         # inputs resident in HBM; nothing here synchronises the host
@@ -528,8 +579,13 @@ def main():
 
         def launch(i, prep):
             q, a_, r_, k_, pl = prep
+            m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True); m2 = torch.cuda.Event(enable_timing=True)
+            m0.record()
             pl.run(a_)
+            m1.record()
             pp = postprocess(out["uout"], out["zout"], n0=2, bits=24, out=pcm[i % 2])
+            m2.record()
+            marks_e2e.append((m0, m1, m2))
             fl = torch.stack([pp["is_nan"].double(), pp["is_silent"].double(), pp["gain"]])
             ev = torch.cuda.Event(); ev.record()
             pl.close()
@@ -549,10 +605,11 @@ def main():
             return ev
 
         arrived = []                             # per step: event after the last byte of its results reached the host buffers
+        marks_e2e = []
         prep = prepare()
         ev = launch(0, prep)
         barrier()
-        arrived.clear()
+        arrived.clear(); marks_e2e.clear()
         # the last step's read-back is not hidden: amortised over the pipelined steps (a dataset run pipelines hundreds)
         n_e2e = max(1, min(a.steps, 12)) if a.length < 0.5 else max(6, min(a.steps, 12))
         t0 = time.perf_counter()
@@ -573,6 +630,8 @@ def main():
         e2e = {"value": string_seconds / float(te[0]), "unit": "string-seconds/s",
                "h2d_bytes_per_step": world * sampler.compact_nbytes(p_host), "d2h_bytes_per_step": world * d2h_bytes,
                "ms_per_step": float(te[0]) * 1e3, "pipelined_steps": n_e2e,
+               "ms_stepper": sum(m[0].elapsed_time(m[1]) for m in marks_e2e) / len(marks_e2e),
+               "ms_postprocess": sum(m[1].elapsed_time(m[2]) for m in marks_e2e) / len(marks_e2e),
                "steady_state": {"value": string_seconds / float(te[1]), "ms_per_step": float(te[1]) * 1e3,
                                 "note": "interval between the host arrival of consecutive steps' results (a dataset run pipelines hundreds of steps: the drain of the last one vanishes)"},
                "note": "all ranks, every step: pinned host compact parameters -> H2D -> plan -> stepper (in-kernel control synthesis) -> "
@@ -583,6 +642,18 @@ def main():
         del out
         torch.cuda.empty_cache()
         sweep = run_sweep(a, [int(x) for x in a.sweep.split(",") if x], rank, world, dev)
+    grouped = None
+    if not a.no_grouped and a.excitation == "pluck":
+        try:
+            import ctypes as _ct
+            pk = _ct.c_double(0.0)
+            if lib.sfdtd_measure_fma_peak(0, _ct.byref(pk)) != 0 or pk.value <= 0:
+                pk.value = 37.2
+            grouped = run_grouped(a, dev, rank, world, pk.value)
+        except Exception as e:
+            if world > 1:
+                raise
+            grouped = {"error": str(e)[:300]}
     drop_in = None
     if rank == 0 and not a.no_drop_in:
         try:
@@ -654,8 +725,8 @@ def main():
         "grid_point_updates_per_s": world * gpu_upd / per_step,
         "mean_operator_widths": {"W_t": Wt_mean, "W_l": Wl_mean},
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e,
-        "fp32": fp32, "drop_in": drop_in, "dataset": ds, "sweep": sweep,
-        "gpu_launches": int(launches), "clocks": clk, "step_ms": [round(x, 2) for x in step_ms],
+        "fp32": fp32, "grouped": grouped, "drop_in": drop_in, "dataset": ds, "sweep": sweep,
+        "plan_create_ms": t_plan * 1e3, "gpu_launches": int(launches), "clocks": clk, "step_ms": [round(x, 2) for x in step_ms],
         "peak_device_memory_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
         "health": {"status_bits": status, "nan_strings": nan_strings,
                    "mean_outer_iters": float(counters[:, 0].sum()) / max(1.0, float(counters[:, 3].sum())),

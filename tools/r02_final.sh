@@ -2,7 +2,7 @@
 # short run of the same workload (0.02 s per string so that ncu's replays stay short)
 set -x
 python bench.py > gpurun_out/r02_final_bench.log 2> gpurun_out/r02_final_bench.err; echo "bench rc=$?"
-B="python bench.py --steps 1 --warmup 1 --fp32-steps 1 --length 0.02 --strings 28416 --no-cpu-baseline --no-e2e --no-drop-in --no-dataset"
+B="python bench.py --steps 1 --warmup 1 --fp32-steps 1 --length 0.02 --strings 28416 --no-cpu-baseline --no-e2e --no-drop-in --no-dataset --no-grouped"
 SFDTD_VERBOSE=1 $B > gpurun_out/r02f_prof_plain.log 2> gpurun_out/r02f_prof_plain.err || exit 1
 grep -h "bucket" gpurun_out/r02f_prof_plain.err | head -24
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02f.csv $B > gpurun_out/r02f_ncu1.log 2>&1
