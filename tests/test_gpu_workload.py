@@ -197,3 +197,26 @@ def test_dataset_layout(tmp_path):
     assert sim["uout"].shape == (2398,) and bool(sim["pluck_mask"])
     sp = np.load(d / "string_params.npz")
     assert set(sp.files) == {"kappa", "alpha", "u0", "v0", "p_a", "f0", "pos", "T60", "target_f0"}
+
+
+@pytest.mark.parametrize("excitation", ["pluck", "hammer"])
+def test_strings_of_257_to_384_rows_match_oracle(oracle, excitation):
+    """f0 52-66 Hz with little stiffness: N_t ~ 280-350, i.e. the 32-lane x 12-row kernel (independent mode) and the
+    32 x 20 grouped kind -- between the fast shapes (<= 256 rows) and the low-f0 fixtures (~ 556 rows)."""
+    from torch_fdtd_string_b200 import sampler
+    cfg = dict(f0_min=52.0, f0_max=66.0, f0_diff_max=2.0, f0_mod_max=0.0, kappa_min=0.0005, kappa_max=0.0015,
+               alpha_min=2.0, alpha_max=4.0, p_a_max=0.004, f0_inf=50.0, alpha_inf=2.0)
+    G, Nt = 4, 42
+    ph = sampler.sample_nsynth_like(2 * G, length=0.05, excitation=excitation, seed=11, cfg=cfg)
+    nt, nl = sampler.derived_grid(torch.minimum(ph["f0_a"], ph["f0_b"]), ph["kappa"], ph["k"], ph["theta_t"], ph["lambda_c"], ph["alpha"])
+    assert int(nt[:G].max()) + 3 > 256 and int(nt.max()) + 3 <= 384, nt
+    p = sampler.to_device(ph, torch.device("cuda"))
+    res = sampler.run_compact(p, G, counters=True, n_run=Nt)
+    torch.cuda.synchronize()
+    assert int(res["status"].max()) == 0
+    ctl = su.device_controls(ph, Nt)
+    ref = gu.run_process(oracle.forward_fn, su.reference_inputs(ph, slice(0, G), Nt, controls=ctl))
+    for k, m in (("uout", "uout"), ("zout", "zout"), ("v_r", "v_r_out"), ("F_H", "F_H_out")):
+        err = gu.rel_l2(res[k][:G, 2:].cpu().numpy(), ref[m].numpy())
+        print(excitation, k, f"{err:.2e}")
+        assert err < 3e-8, (excitation, k, err)
