@@ -685,12 +685,12 @@ def main():
         hbm_peak = 6650.0; hbm_src = "of fallback"
     traffic = None
     try:   # DRAM bytes per string-step of the dominant kernel from the committed ncu --set full capture, scaled to this call
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02f_f64.json")))
         traffic = tr["dram_bytes_per_string_step"] * B * (Nt - 2)
     except Exception:
         pass
     roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
-                "traffic": traffic, "traffic_unit": "DRAM bytes per call (ncu dram__bytes_read+write per string-step of the largest bucket kernel x string-steps of the call; profiles/ncu_traffic_r02.json)",
+                "traffic": traffic, "traffic_unit": "DRAM bytes per call (ncu dram__bytes_read+write per string-step of the largest bucket kernel x string-steps of the call; profiles/ncu_traffic_r02f_f64.json)",
                 "peak_source": peak_src, "peak_nominal": 37.2, "frac_of_nominal": achieved / 37.2,
                 "flops_per_string_step": flops / (B * (Nt - 2)),
                 # the same formula on the rows the kernel actually solves (own grid N_t+3 / N_l+3 instead of the batch-max

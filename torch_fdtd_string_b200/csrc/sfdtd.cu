@@ -28,8 +28,13 @@
 //     the any-over-batch convergence votes (string.cpp:252-253, hammer.cpp:51).  The widths come from a
 //     prepass table.  A group without bowed/hammered strings needs no votes (the second fixed-point
 //     pass of an unforced string reproduces the first), so its strings run fully independently
-//     ("independent mode", any warp, no CTA barrier); a group with forced strings runs as one CTA with
-//     __syncthreads_or votes ("grouped mode").
+//     ("independent mode", any warp, no CTA barrier); a group with forced strings runs as one thread-block
+//     cluster of 128-thread CTAs whose votes travel as 32-bit OR words through distributed shared memory
+//     ("grouped mode").
+//   * The stepper is templated on its arithmetic type: double (SFDTD_F64, the parity mode) and float (SFDTD_F32, the
+//     reference's `precision: single`): state rows, working set, solves and outputs are of that type, the per-step
+//     scalar table / bow window / hammer loop are evaluated in double in both builds, and an fp32 call takes its grid
+//     sizes from the reference's float32 evaluation of get_derived_vars.
 //   * Scheduling (independent mode): the grid of a bucket is what is resident at once, and every warp pulls its next
 //     (time slice, set of 32/L strings) item from a per-bucket counter -- the hardest sets first, each for the whole call,
 //     the sets of the last round in time slices whose state rows pass from warp to warp through global memory with a
