@@ -91,7 +91,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
@@ -101,12 +101,16 @@ class ClockSampler:
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        sm.sort()
-        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
-                    samples=len(sm), reasons=sorted(reasons))
+        sm.sort(); pw.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_min_mhz=(sm[0] if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                    power_w=(pw[len(pw) // 2] if pw else None), samples=len(sm), reasons=sorted(reasons))
 
 
 def reference_arm(a, rank):
@@ -565,16 +569,15 @@ def main():
         copy_stream = torch.cuda.Stream(device=dev)
         d2h_bytes = 3 * B * pitch + 3 * B * 8
 
-        side = torch.cuda.Stream(device=dev)     # inputs + plan of the NEXT step are prepared here while the current one runs
-        main = torch.cuda.current_stream()
-
         def prepare():
-            # host -> device copy of the step's inputs and the plan (prepass kernel, its small read-back, bucketing): on the side
-            # stream, so that the host never waits for the stepper here and the GPU never waits for the host
-            with torch.cuda.stream(side):
-                q = sampler.to_device(ph, dev, non_blocking=True)
-                a_, r_, k_ = sampler.compact_args(q, GROUP, skip_aux=a.skip_aux, out=out, aux_outputs=False)
-                pl = Plan(a_)                    # synchronises the side stream only
+            # inputs and plan of a step are prepared once the previous call has finished (its read-back still runs on the copy
+            # stream): H2D of the compact parameters, prepass kernel (results through mapped pinned memory: a device->host copy
+            # would queue behind the bulk PCM read-back), bucketing.  Measured alternatives (tools/r02_e2e_diag.sh, 0.5 s strings,
+            # 1480 ms stepper): prepared beside the running call on a side stream the stepper takes 1554-1638 ms and a step
+            # 1626-1727 ms; prepared in the gap 1493 / 1537 ms.
+            q = sampler.to_device(ph, dev, non_blocking=True)
+            a_, r_, k_ = sampler.compact_args(q, GROUP, skip_aux=a.skip_aux, out=out, aux_outputs=False)
+            pl = Plan(a_)
             return (q, a_, r_, k_, pl)           # (kept alive by the caller until the step's kernels have completed)
 
         def launch(i, prep):
@@ -593,7 +596,7 @@ def main():
                 copy_stream.wait_event(ev)
                 flags_h.copy_(fl, non_blocking=True)
                 j = 0
-                for kx in ("u", "z", "w"):
+                for kx in (() if os.environ.get("SFDTD_BENCH_NO_D2H") else ("u", "z", "w")):      # (diagnostics knob)
                     src = pcm[i % 2][kx]
                     for r0 in range(0, B, chunk_rows):
                         r1 = min(B, r0 + chunk_rows)
@@ -612,15 +615,14 @@ def main():
         arrived.clear(); marks_e2e.clear()
         # the last step's read-back is not hidden: amortised over the pipelined steps (a dataset run pipelines hundreds)
         n_e2e = max(1, min(a.steps, 12)) if a.length < 0.5 else max(6, min(a.steps, 12))
+        clocks_e2e = ClockSampler(local_rank); clocks_e2e.start()
         t0 = time.perf_counter()
-        prep = prepare()
         for i in range(n_e2e):
-            held = prep
+            prep = prepare()
             ev = launch(i + 1, prep)             # stepper + post-processing of step i+1 on the main stream, read-back on the copy stream
-            if i + 1 < n_e2e:
-                prep = prepare()                 # overlaps the stepper of step i+1
             ev.synchronize()                     # one call in flight: a launch queued behind a running call slows it down (--async-steps)
         barrier()
+        clk_e2e = clocks_e2e.stop()
         # value: wall clock of the n pipelined steps incl. the un-hidden read-back of the last one (cold-start + drain);
         # steady state: interval between the arrival of the first and of the last step's results on the host
         steady = arrived[0].elapsed_time(arrived[-1]) * 1e-3 / max(1, len(arrived) - 1) if len(arrived) > 1 else float("nan")
@@ -632,10 +634,12 @@ def main():
                "ms_per_step": float(te[0]) * 1e3, "pipelined_steps": n_e2e,
                "ms_stepper": sum(m[0].elapsed_time(m[1]) for m in marks_e2e) / len(marks_e2e),
                "ms_postprocess": sum(m[1].elapsed_time(m[2]) for m in marks_e2e) / len(marks_e2e),
+               "clocks": clk_e2e,
                "steady_state": {"value": string_seconds / float(te[1]), "ms_per_step": float(te[1]) * 1e3,
                                 "note": "interval between the host arrival of consecutive steps' results (a dataset run pipelines hundreds of steps: the drain of the last one vanishes)"},
-               "note": "all ranks, every step: pinned host compact parameters -> H2D -> plan -> stepper (in-kernel control synthesis) -> "
-                       "device NaN/silence/gain + PCM_24 quantisation -> D2H of output-u/-z/sum PCM (copy stream, overlapping the next step)"}
+               "note": "all ranks, every step: pinned host compact parameters -> H2D -> plan -> stepper "
+                       "(in-kernel control synthesis) -> device NaN/silence/gain + PCM_24 quantisation -> D2H of output-u/-z/sum PCM (copy "
+                       "stream, overlapping the next step)"}
 
     sweep = None
     if a.sweep:

@@ -268,8 +268,12 @@ __device__ __forceinline__ int clampN(double v) { return (int)fmin(fmax(v, 0.0),
 // Also a per-string estimate of the nonlinearity  phi/h^2 Lambda^2  of the first step (from state row n-1): it predicts
 // how many block sweeps the string needs, and the host sorts the strings of a launch by it so that the strings
 // sharing a warp converge in about the same number of sweeps.
+// The results also go to mapped pinned host memory (hNt ... hHam, written by the kernel itself over PCIe): the host reads them
+// after one stream synchronisation without a device->host copy, which would queue behind whatever bulk read-back the caller
+// has in flight on the copy engine.
 template <typename T>
-__global__ void sfdtd_prepass_kernel(const __grid_constant__ KArgs A, int32_t *maxNt, int32_t *maxNl, float *est) {
+__global__ void sfdtd_prepass_kernel(const __grid_constant__ KArgs A, int32_t *maxNt, int32_t *maxNl, float *est,
+                                     int32_t *hNt, int32_t *hNl, float *hEst, uint8_t *hBow, uint8_t *hHam) {
     const int b = blockIdx.x;
     const int Nt = A.a.Nt;
     double fm = INFINITY;
@@ -299,6 +303,8 @@ __global__ void sfdtd_prepass_kernel(const __grid_constant__ KArgs A, int32_t *m
         const double phi = ((d.gamma * d.gamma) * A.k2) * (alpha * alpha - 1) / 4;
         const double n2 = d.Nt * d.Nt;
         est[b] = (float)(phi * n2 * n2 * dm * dm);
+        hNt[b] = maxNt[b]; hNl[b] = maxNl[b]; hEst[b] = est[b];
+        hBow[b] = A.a.bow_mask[b]; hHam[b] = A.a.hammer_mask[b];
     }
 }
 
@@ -1803,6 +1809,23 @@ double env_dbl(const char *name, double dflt) { const char *v = getenv(name); re
 // different plans in flight on different caller streams must not serialise behind each other); released streams go back to
 // a per-device free list (work still queued on them stays ordered).
 std::mutex g_mu;
+// mapped pinned result buffers of the prepass, pooled per process (one per plan being created; a few hundred KB each; freeing
+// pinned memory synchronises the device, so they are kept)
+struct PinBuf { void *p; size_t n; bool busy; };
+std::vector<PinBuf> g_pin;
+void *pin_acquire(size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (PinBuf &b : g_pin) if (!b.busy && b.n >= n) { b.busy = true; return b.p; }
+    PinBuf nb; nb.n = std::max(n, (size_t)1 << 20); nb.busy = true; nb.p = nullptr;
+    if (cudaHostAlloc(&nb.p, nb.n, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    g_pin.push_back(nb);
+    return nb.p;
+}
+void pin_release(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (PinBuf &b : g_pin) if (b.p == p) b.busy = false;
+}
 std::map<int, std::vector<cudaStream_t>> g_free_streams;
 std::map<int, bool> g_pool_ready;
 
@@ -1882,7 +1905,8 @@ struct sfdtd_plan {
     int32_t B = 0, group_size = 0, Nt = 0, Nx_t1 = 0, Nx_l1 = 0, n_groups = 0, dtype = 0;
     uint32_t flags = 0;
     std::vector<Launch> launches;
-    char *block = nullptr;           // one device allocation: maxNl | ids | ctas | queue words | width table | u_H carry
+    int32_t *d_max = nullptr;        // prepass output [N_t maxima | N_l maxima] (the steppers read the N_l half)
+    char *block = nullptr;           // one device allocation: (unused) | ids | ctas | queue words | width table | u_H carry
     int32_t *d_maxNl = nullptr, *d_ids = nullptr, *d_queue = nullptr, *d_wtab = nullptr;
     CtaDesc *d_ctas = nullptr;
     double *d_uH = nullptr;
@@ -1933,6 +1957,7 @@ extern "C" int sfdtd_plan_destroy(sfdtd_plan *plan, void *cuda_stream) {
     cudaGetDevice(&prev);
     if (prev != plan->dev) cudaSetDevice(plan->dev);
     if (plan->block) cudaFreeAsync(plan->block, (cudaStream_t)cuda_stream);
+    if (plan->d_max) cudaFreeAsync(plan->d_max, (cudaStream_t)cuda_stream);
     if (plan->fork) cudaEventDestroy(plan->fork);
     for (cudaEvent_t e : plan->joins) cudaEventDestroy(e);
     {
@@ -1957,9 +1982,11 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
     sfdtd_plan *P = new sfdtd_plan();
     int32_t *d_max = nullptr; float *d_est = nullptr;
     const int n_groups = (a.B + a.group_size - 1) / a.group_size;
-    std::vector<float> h_est(a.B);
-    std::vector<int32_t> h_max(2 * (size_t)a.B), h_ids;
-    std::vector<uint8_t> h_bow(a.B), h_ham(a.B);
+    // prepass results in mapped pinned memory: h_max = [N_t maxima | N_l maxima], h_est, h_bow, h_ham
+    const size_t Bp = ((size_t)a.B + 3) & ~(size_t)3;
+    void *pin = nullptr;
+    int32_t *h_max = nullptr; float *h_est = nullptr; uint8_t *h_bow = nullptr, *h_ham = nullptr;
+    std::vector<int32_t> h_ids;
     std::vector<CtaDesc> h_ctas;
     // run-time knobs (read once per plan)
     // smallest longitudinal allocation class: a coarser one merges buckets (one work queue balances more strings) for more
@@ -2004,14 +2031,13 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
     // ---- prepass: per-string grid maxima and difficulty estimate; ONE device->host read ----
     CK(cudaMallocAsync((void **)&d_max, sizeof(int32_t) * 2 * (size_t)a.B, stream));
     CK(cudaMallocAsync((void **)&d_est, sizeof(float) * (size_t)a.B, stream));
-    if (dt) sfdtd_prepass_kernel<float><<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B, d_est);
-    else sfdtd_prepass_kernel<double><<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B, d_est);
+    pin = pin_acquire(Bp * (2 * sizeof(int32_t) + sizeof(float) + 2));
+    if (!pin) { snprintf(g_err, sizeof g_err, "cudaHostAlloc of the prepass result buffer failed"); rc = SFDTD_ERR_CUDA; goto done; }
+    h_max = (int32_t *)pin; h_est = (float *)(h_max + 2 * Bp); h_bow = (uint8_t *)(h_est + Bp); h_ham = h_bow + Bp;
+    if (dt) sfdtd_prepass_kernel<float><<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B, d_est, h_max, h_max + Bp, h_est, h_bow, h_ham);
+    else sfdtd_prepass_kernel<double><<<a.B, 128, 0, stream>>>(K, d_max, d_max + a.B, d_est, h_max, h_max + Bp, h_est, h_bow, h_ham);
     g_launches++;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h_max.data(), d_max, sizeof(int32_t) * 2 * (size_t)a.B, cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(h_est.data(), d_est, sizeof(float) * (size_t)a.B, cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(h_bow.data(), a.bow_mask, a.B, cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(h_ham.data(), a.hammer_mask, a.B, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
 
     // ---- bucketing ----
@@ -2027,7 +2053,7 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
         // every padded row is forced in the manufactured mode (string.cpp:227-232)
         auto rows_of = [&](int b) { return manuf ? Wt : std::min(Wt, h_max[b] + 3 + (h_bow[b] ? 8 : 0)); };
         // lanes that keep the longitudinal loops short
-        auto lanes_of = [&](int b) { return std::max(std::min(32, wl_class(long_rows(h_max[a.B + b])) / lane_div), min_lanes_env); };
+        auto lanes_of = [&](int b) { return std::max(std::min(32, wl_class(long_rows(h_max[Bp + b])) / lane_div), min_lanes_env); };
         if (!forced) {
             for (int s = 0; s < G; s++) {
                 const int b = g0 + s, rows = rows_of(b), min_lanes = lanes_of(b);
@@ -2038,7 +2064,7 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
                     snprintf(g_err, sizeof g_err, "string %d: %d transverse rows are outside the built kernel set", b, rows);
                     rc = SFDTD_ERR_UNSUPPORTED; goto done;
                 }
-                ib[{pick, wl_class(long_rows(h_max[a.B + b]), wl_min)}].ids.push_back(b);   // the allocation class may be coarser than the lane class
+                ib[{pick, wl_class(long_rows(h_max[Bp + b]), wl_min)}].ids.push_back(b);   // the allocation class may be coarser than the lane class
             }
             continue;
         }
@@ -2087,7 +2113,7 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
                 const GShape sh = g_gshape[kind][cd.cls];
                 const int nslots = threads / sh.L;
                 size_t dbl = GB_DOUBLES + xax_doubles(a.Nx_t1, true) + (size_t)nslots * slot_fixed_doubles(sh.L, sh.ET, true, tsz) + (size_t)(nslots + 2) / 2 + 2;
-                for (int s = 0; s < nslots; s++) dbl += slot_long_doubles(long_rows(h_max[a.B + cd.str[std::min(s, cd.n - 1)]]), true, sh.L, tsz);
+                for (int s = 0; s < nslots; s++) dbl += slot_long_doubles(long_rows(h_max[Bp + cd.str[std::min(s, cd.n - 1)]]), true, sh.L, tsz);
                 smem = std::max(smem, dbl * sizeof(double) + 16);
             }
             if (kind == 0 || smem <= 227 * 1024 || per_big == 1) break;
@@ -2200,7 +2226,8 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
         CK(cudaMallocAsync((void **)&P->block, total, stream));
         P->d_maxNl = (int32_t *)(P->block + o_max); P->d_ids = (int32_t *)(P->block + o_ids); P->d_ctas = (CtaDesc *)(P->block + o_cta);
         P->d_queue = (int32_t *)(P->block + o_q); P->d_wtab = (int32_t *)(P->block + o_w); P->d_uH = (double *)(P->block + o_uh);
-        CK(cudaMemcpyAsync(P->d_maxNl, d_max + a.B, sizeof(int32_t) * a.B, cudaMemcpyDeviceToDevice, stream));
+        P->d_max = d_max; d_max = nullptr;           // (no device-to-device copy: it would queue on a copy engine like the read-backs)
+        P->d_maxNl = P->d_max + a.B;
         if (!h_ids.empty()) CK(cudaMemcpyAsync(P->d_ids, h_ids.data(), sizeof(int32_t) * h_ids.size(), cudaMemcpyHostToDevice, stream));
         if (!h_ctas.empty()) CK(cudaMemcpyAsync(P->d_ctas, h_ctas.data(), sizeof(CtaDesc) * h_ctas.size(), cudaMemcpyHostToDevice, stream));
         CK(cudaStreamSynchronize(stream));        // the host vectors go out of scope; still before any stepper kernel is queued
@@ -2226,6 +2253,7 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
         }
     }
 done:
+    pin_release(pin);
     if (d_max) cudaFreeAsync(d_max, stream);
     if (d_est) cudaFreeAsync(d_est, stream);
     if (rc != SFDTD_OK) { sfdtd_plan_destroy(P, stream); return rc; }
