@@ -73,3 +73,40 @@ def test_files_match_the_reference_run(tmp_path):
             q = np.clip(np.rint(ref * 8388608.0), -8388608, 8388607).astype(np.int64)
             assert np.abs(v - q).max() <= 1, (wname, int(np.abs(v - q).max()))          # a 1e-12 difference can flip one rounding
             assert (v != q).mean() < 0.01
+
+
+def test_load_config_overrides_reach_the_stepper_and_the_files(tmp_path):
+    """task.load_config (reference README 1.3, src/task/simulate.py:164-185): predefined f0 / hammer-velocity curves as npy
+    files -> the stepper's table mode; the saved f0 is the loaded curve pre-corrected by each string's Fletcher factor, the
+    saved hammer displacement starts from the loaded strike profile, and the run differs from the un-conditioned one."""
+    from torch_fdtd_string_b200 import dataset, sampler
+    p = presets.PRESETS["nsynth"]
+    sr, length, B = p["sr"], 0.02, 6
+    Nt = int(sr * length)
+    theta_t = sampler.get_theta(0.03, 98.0, sr)
+    pre = tmp_path / "preset"; pre.mkdir()
+    f0 = 220.0 + 10.0 * np.sin(np.linspace(0, 3, Nt // 2))                  # shorter than the run: edge-padded like the reference
+    prof = np.zeros(Nt); prof[5:8] = 1.0
+    np.save(pre / "string-f0.npy", f0); np.save(pre / "hammer-v_H.npy", prof)
+    over = dataset.load_overrides(str(pre), Nt)
+    assert sorted(over) == ["hammer-v_H", "string-f0"] and over["string-f0"].shape == (Nt,) and over["string-f0"][-1] == f0[-1]
+    outs = {}
+    for tag, ov in (("plain", None), ("cond", over)):
+        torch.manual_seed(5)
+        src = dataset.reference_source(B, sr, length, "hammer", theta_t, p["f0_inf"], p["alpha_inf"], p["lambda_c"], "double",
+                                       p["string_kwargs"], p["bow_kwargs"], p["hammer_kwargs"], False, p["relative_order"],
+                                       redraw_v_H=bool(ov))
+        d = tmp_path / tag
+        st = dataset.generate(str(d), B, B, "hammer", sr, length, precision="double", source=src, full_layout=True, overrides=ov,
+                              skip_silence=False)
+        assert st["strings"] == B and st["written"] >= B - 1
+        outs[tag] = d
+    d = outs["cond"] / sorted(os.listdir(outs["cond"]))[0]
+    sp = np.load(d / "string_params.npz"); hp = np.load(d / "hammer_params.npz"); sim = np.load(d / "simulation.npz")
+    w0 = float(sampler.fletcher_w0(torch.tensor([float(sp["kappa"])], dtype=torch.float64))[0])
+    np.testing.assert_allclose(sp["f0"], over["string-f0"].astype(np.float32).astype(np.float64) / w0, rtol=1e-12)
+    assert np.isfinite(sim["uout"]).all() and np.abs(sim["uout"]).max() > 0
+    # the hammer is thrown at samples 5..7 instead of sample 1: nothing touches the string before
+    assert np.abs(sim["F_H_out"][:3]).max() == 0.0
+    d0 = outs["plain"] / sorted(os.listdir(outs["plain"]))[0]
+    assert gu.rel_l2(np.load(d0 / "simulation.npz")["uout"], sim["uout"]) > 1e-3

@@ -80,3 +80,44 @@ def test_successive_batches_continue_the_stream():
     g = gu.load_golden("pluck_b3")
     assert np.array_equal(a["kappa"].numpy(), g["kappa"].reshape(-1))
     assert not np.array_equal(a["kappa"].numpy(), b["kappa"].numpy())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference checkout")
+def test_load_config_overrides_match_the_reference_modules():
+    """task.load_config (reference src/task/simulate.py:164-185): the reference's String / Bow / Hammer modules after
+    dump_parameter('f0' | 'v_b' | 'v_H', curve) against dataset.apply_overrides on the RNG-compatible compact batch."""
+    sys.path.insert(0, os.path.join(os.path.dirname(gu.GOLDEN_DIR), "..", "oracle"))
+    import ref_driver
+    ref_driver.import_reference()
+    import src.model.simulator as rs
+    from torch_fdtd_string_b200 import dataset
+    p = presets.PRESETS["nsynth"]
+    sr, length, B = p["sr"], 0.01, 3
+    Nt = int(sr * length)
+    theta_t = sampler.get_theta(0.03, 98.0, sr)
+    rng = np.random.RandomState(0)
+    over = {"string-f0": 200.0 + 20.0 * np.linspace(0, 1, Nt) + rng.rand(Nt), "bow-v_b": 0.3 + 0.05 * rng.rand(Nt),
+            "hammer-v_H": np.concatenate([np.zeros(3), np.ones(2), np.zeros(Nt - 5)])}
+    # the reference: modules, then the dumps in simulate()'s order (after all three are constructed)
+    torch.manual_seed(77)
+    bm, hm = torch.zeros(B, dtype=torch.bool), torch.ones(B, dtype=torch.bool)
+    pm = ~(bm | hm)
+    string = rs.String(1 / sr, theta_t, p["lambda_c"], sr, length, p["f0_inf"], p["alpha_inf"], B, "double", False, pm, hm, "batch", False,
+                       **p["string_kwargs"])
+    bow = rs.Bow(sr, length, B, "double", "batch", **p["bow_kwargs"])
+    hammer = rs.Hammer(sr, length, B, "double", 1 / sr, "batch", **p["hammer_kwargs"])
+    string.dump_parameter("f0", over["string-f0"]); bow.dump_parameter("v_b", over["bow-v_b"]); hammer.dump_parameter("v_H", over["hammer-v_H"])
+    with torch.no_grad():
+        sp, bp, hp = string(), bow(), hammer()
+    f0_ref, vb_ref, uH_ref = sp[7].numpy(), bp[1].numpy(), hp[2].numpy()          # after the two state tensors: kappa alpha u0 v0 p_a f0
+    # this package
+    torch.manual_seed(77)
+    q = sampler_ref.sample_reference(B, "hammer", sr, length, theta_t, p["f0_inf"], p["alpha_inf"], p["lambda_c"], precision="double",
+                                     string_kwargs=p["string_kwargs"], bow_kwargs=p["bow_kwargs"], hammer_kwargs=p["hammer_kwargs"],
+                                     redraw_v_H=True)
+    ctl = dataset.apply_overrides(q, dict(sampler.expand_controls(q, torch.device("cpu"))), over)
+    assert np.abs(ctl["f0"].numpy() - f0_ref).max() <= 1e-12 * np.abs(f0_ref).max()
+    assert np.array_equal(ctl["v_b"].numpy(), np.broadcast_to(over["bow-v_b"], (B, Nt))) and np.array_equal(vb_ref, ctl["v_b"].numpy())
+    assert np.abs(ctl["u_H"].numpy() - uH_ref).max() <= 1e-18
+    # the other draws are untouched by the dumps
+    assert np.array_equal(q["kappa"].numpy(), sp[2].detach().numpy().reshape(-1))

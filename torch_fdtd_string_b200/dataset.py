@@ -96,20 +96,80 @@ def native_source(batch_size, sr, length, excitation, seed, cfg=None):
 
 
 def reference_source(batch_size, sr, length, excitation, theta_t, f0_inf, alpha_inf, lambda_c, precision="double",
-                     string_kwargs=None, bow_kwargs=None, hammer_kwargs=None, manufactured=False, relative_order=4):
+                     string_kwargs=None, bow_kwargs=None, hammer_kwargs=None, manufactured=False, relative_order=4,
+                     redraw_v_H=False):
     """the reference's draws from the GLOBAL torch RNG (seed it like reference run.py:75 first); must be called for every
     batch index in order, on every rank"""
     def draw(it):
         return sampler_ref.sample_reference(batch_size, excitation, sr, length, theta_t, f0_inf, alpha_inf, lambda_c, precision,
-                                            string_kwargs, bow_kwargs, hammer_kwargs, manufactured, relative_order)
+                                            string_kwargs, bow_kwargs, hammer_kwargs, manufactured, relative_order,
+                                            redraw_v_H=redraw_v_H)
     draw.sequential = True
     return draw
+
+
+# ---- task.load_config: predefined control curves (reference src/task/simulate.py:164-185, README 1.3) ----------------------
+OVERRIDE_KEYS = ("string-f0", "bow-x_b", "bow-v_b", "bow-F_b", "bow-wid", "hammer-v_H", "hammer-u_H")
+
+
+def load_overrides(path, total_size):
+    """``{model}-{param}.npy`` files of a preset directory -> {key: (total_size,) float64 array}, padded with the edge value
+    or cut like the reference does (simulate.py:166-172).  Parameters the reference could dump but that are not time curves
+    (or re-initialise the state: ``string-plucked``) are refused."""
+    import glob
+    out = {}
+    for f in sorted(glob.glob(os.path.join(path, "*.npy"))):
+        val = np.load(f)
+        if val.shape[-1] < total_size:
+            val = np.pad(val, (0, total_size - val.shape[-1]), mode="edge")
+        else:
+            val = val[:total_size]
+        model, param = os.path.basename(f).split(".")[0].split("-")
+        key = f"{model.lower()}-{param}"
+        if key not in OVERRIDE_KEYS:
+            raise NotImplementedError(f"task.load_config: {os.path.basename(f)} ({key}) is not built; supported: {', '.join(OVERRIDE_KEYS)}")
+        out[key] = np.asarray(val, dtype=np.float64)
+    return out
+
+
+def apply_overrides(p, ctl, overrides):
+    """Replaces control curves of one batch by the loaded ones, like ``dump_parameter`` of the reference's modules
+    (src/model/simulator.py:98-112, 441-446, 555-564): every string of the batch gets the same curve.  p: compact batch,
+    ctl: dict of (B,Nt) curves (sampler.expand_controls) on p's device; returns ctl (modified in place)."""
+    B, Nt = p["B"], ctl["f0"].size(1)
+    dev = ctl["f0"].device
+    for key, val in overrides.items():
+        v = torch.from_numpy(np.ascontiguousarray(val[:Nt])).to(dev)
+        if key == "string-f0":
+            # String.dump_parameter casts the dump to float32 and pre-corrects it by the Fletcher factor of each string
+            v = v.float().double().view(1, -1)
+            w0 = sampler.fletcher_w0(p["kappa"].to(dev)).view(-1, 1)
+            f0 = v / w0
+            lo = p.get("f0_inf_corrected")
+            if lo is not None:
+                assert float(f0.min()) >= lo, (float(f0.min()), lo)          # simulator.py:109
+            ctl["f0"] = f0.expand(B, Nt).contiguous()
+        elif key in ("bow-x_b", "bow-v_b", "bow-F_b", "bow-wid"):
+            ctl[key[4:]] = v.view(1, -1).expand(B, Nt).contiguous()
+        elif key == "hammer-u_H":
+            ctl["u_H"] = v.view(1, -1).expand(B, Nt).contiguous()
+        elif key == "hammer-v_H":
+            # initialize_velocity(profile): v_H = (a fresh draw) x profile; u_H = M_HD on samples 0, 1 + k v_H (simulator.py:570-578)
+            prof = v.float().double().view(1, -1)
+            v_H = p["v_H_redrawn"].to(dev).view(-1, 1) * prof
+            u_H = torch.zeros(B, Nt, dtype=torch.float64, device=dev)
+            u_H[:, :2] += -1e-3
+            ctl["u_H"] = u_H + p["k"] * v_H
+        else:
+            raise NotImplementedError(key)
+    return ctl
 
 
 def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000, length=1.0, seed=1234,
              precision="double", normalize_output=True, skip_silence=True, silence_threshold=-23.0, save=True,
              randomize_name=False, batches_per_call=64, rank=0, world_size=1, device=None, surface_integral=True,
-             sampler_cfg=None, time_log=False, num_workers=4, source=None, full_layout=False, manufactured=False):
+             sampler_cfg=None, time_log=False, num_workers=4, source=None, full_layout=False, manufactured=False,
+             overrides=None):
     """Generates ``num_samples // batch_size`` reference batches (reference run.py:109) and writes the kept strings.
     The per-string files (three wavs, four compressed archives: ~0.3 s of zlib per string on one core) are written by
     ``num_workers`` threads (``proc.num_workers`` of the reference's config; zlib releases the GIL) while the GPU runs the
@@ -171,12 +231,27 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
         uH = torch.zeros(B, Nt, **f64)
         uH[:, :2] = -1e-3
         uH[:, 1] += p_host["k"] * p["v_H"]
-        args, res, keep_alive = build_args(
-            su, sz, u_H=uH, kappa=p["kappa"], alpha=p["alpha"], pos=p["pos"], T60=p["T60"], phi_0=p["phi_0"], phi_1=p["phi_1"],
-            x_H=p["x_H"], w_H=p["w_H"], M_r=p["M_r"], alpha_H=p["alpha_H"], bow_mask=p["bow_mask"], hammer_mask=p["hammer_mask"],
-            k=p_host["k"], theta_t=p_host["theta_t"], lambda_c=p_host["lambda_c"], relative_order=p_host["relative_order"],
-            Nt=Nt, group_size=batch_size, synth=sampler.synth_dict(p), surface_integral=surface_integral,
-            save_state=full_layout, manufactured=manufactured, p_a=p["p_a"])
+        ctl_tab = None
+        if overrides:
+            # task.load_config: the curves are materialised as (B,Nt) tables with the loaded ones substituted (the stepper's
+            # table mode); everything else is unchanged
+            pq = dict(p); pq["B"] = B
+            for kx in ("v_H_redrawn",):
+                if kx in p_host:
+                    pq[kx] = p_host[kx]
+            pq["f0_inf_corrected"] = p_host.get("f0_inf_corrected")
+            ctl_tab = apply_overrides(pq, dict(sampler.expand_controls(pq, device)), overrides)
+            uH = ctl_tab["u_H"].to(f64["dtype"]).contiguous()
+        common = dict(kappa=p["kappa"], alpha=p["alpha"], pos=p["pos"], T60=p["T60"], phi_0=p["phi_0"], phi_1=p["phi_1"],
+                      x_H=p["x_H"], w_H=p["w_H"], M_r=p["M_r"], alpha_H=p["alpha_H"], bow_mask=p["bow_mask"],
+                      hammer_mask=p["hammer_mask"], k=p_host["k"], theta_t=p_host["theta_t"], lambda_c=p_host["lambda_c"],
+                      relative_order=p_host["relative_order"], Nt=Nt, group_size=batch_size, surface_integral=surface_integral,
+                      save_state=full_layout, manufactured=manufactured, p_a=p["p_a"])
+        if ctl_tab is None:
+            args, res, keep_alive = build_args(su, sz, u_H=uH, synth=sampler.synth_dict(p), **common)
+        else:
+            args, res, keep_alive = build_args(su, sz, u_H=uH, f0=ctl_tab["f0"], x_b=ctl_tab["x_b"], v_b=ctl_tab["v_b"],
+                                               F_b=ctl_tab["F_b"], wid=ctl_tab["wid"], **common)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         plan = Plan(args)
         e0.record()
@@ -203,7 +278,10 @@ def generate(save_dir, num_samples, batch_size=24, excitation="pluck", sr=48000,
         sub = dict(p)
         for kx in sampler.SYNTH_KEYS:
             sub[kx] = p[kx].index_select(0, idx)
-        ctl = synth_controls(sampler.synth_dict(sub), len(kept), Nt, device)                  # the curves the stepper used
+        if ctl_tab is None:
+            ctl = synth_controls(sampler.synth_dict(sub), len(kept), Nt, device)              # the curves the stepper used
+        else:
+            ctl = {k: ctl_tab[k].index_select(0, idx) for k in ("f0", "x_b", "v_b", "F_b")}
         ctl_h = {k: ctl[k].cpu().numpy() for k in ("f0", "x_b", "v_b", "F_b")}
         ctl_h["u_H"] = uH.index_select(0, idx).cpu().numpy()
         f0 = ctl_h["f0"]

@@ -13,7 +13,8 @@ reference's result-file layout (``dataset.py``).
 Under ``torchrun`` every rank takes its share of the batches (``proc.gpus`` is ignored then); otherwise the first entry of
 ``proc.gpus`` selects the device.  What the reference's CLI can do and this one refuses, loudly: ``proc.cpu=true`` (there is
 no CPU path), ``proc.{evaluate,summarize,process_training_data,train,test}`` (not part of the time-stepping path),
-``task.load_config``, ``task.plot`` / ``plot_state`` (ignored with a notice).
+``task.plot`` / ``plot_state`` (ignored with a notice).  ``task.load_config`` (predefined f0 / bow / hammer curves as npy files)
+is honoured through the stepper's table mode (``dataset.load_overrides`` / ``apply_overrides``).
 
 Parameters are drawn by ``sampler_ref`` -- the reference's String / Bow / Hammer draws restated RNG-stream compatibly, so
 ``proc.seed`` reproduces the reference's dataset (all sampling modes, pluck profiles, the manufactured initial condition).
@@ -237,8 +238,6 @@ def main(argv=None):
     if proc.get("simulate"):
         if rank == 0:
             backup_code()
-        if task.get("load_config") is not None:
-            raise NotImplementedError("task.load_config (npy parameter dumps) is not built")
         for key in ("plot", "plot_state"):
             if task.get(key):
                 print(f"[run] task.{key}=true ignored: plotting is outside the time-stepping path")
@@ -249,12 +248,17 @@ def main(argv=None):
         # parameter draws: the reference's own, RNG-stream compatible (proc.seed gives the reference's dataset); set
         # SFDTD_SAMPLER=native for the per-batch-seeded compact sampler
         source = None
+        overrides = None
+        if task.get("load_config") is not None:
+            # predefined conditions (reference README 1.3, src/task/simulate.py:164-185): {model}-{param}.npy curves
+            overrides = dataset.load_overrides(str(task["load_config"]), int(float(task["length"]) * int(task["sr"])))
+            print(f"[run] task.load_config: {sorted(overrides)}")
         if os.environ.get("SFDTD_SAMPLER", "reference") == "reference":
             sk, hk, bk, theta_t = reference_kwargs(task)
             source = dataset.reference_source(
                 int(task["batch_size"]), int(task["sr"]), float(task["length"]), p["model_name"], theta_t, task["f0_inf"],
                 task["alpha_inf"], task["lambda_c"], task["precision"], sk, bk, hk, bool(task.get("manufactured")),
-                task["relative_order"])
+                task["relative_order"], redraw_v_H=bool(overrides and "hammer-v_H" in overrides))
         stats = dataset.generate(
             p["save_dir"], int(task["num_samples"]), int(task["batch_size"]), p["model_name"], int(task["sr"]),
             float(task["length"]), int(proc["seed"]), task["precision"], bool(task["normalize_output"]),
@@ -262,7 +266,8 @@ def main(argv=None):
             randomize_name=bool(task["randomize_name"]), rank=rank, world_size=world,
             surface_integral=bool(task["surface_integral"]), sampler_cfg=(sampler_config(task) if source is None else None),
             time_log=True, num_workers=int(proc.get("num_workers") or 1), source=source,
-            full_layout=os.environ.get("SFDTD_COMPACT_RESULTS", "0") != "1", manufactured=bool(task.get("manufactured")))
+            full_layout=os.environ.get("SFDTD_COMPACT_RESULTS", "0") != "1", manufactured=bool(task.get("manufactured")),
+            overrides=overrides)
         print(f"[run] rank {rank}/{world}: {stats}")
     return 0
 

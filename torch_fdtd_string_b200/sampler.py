@@ -225,10 +225,12 @@ def concat(parts):
     for q in parts[1:]:
         assert (q["Nx_t1"], q["Nx_l1"], q["Nt"]) == (p0["Nx_t1"], p0["Nx_l1"], p0["Nt"])
     out = dict(p0)
-    extra = [kx for kx in ("target_f0_a", "target_f0_b", "u0") if all(kx in q for q in parts)]
+    extra = [kx for kx in ("target_f0_a", "target_f0_b", "u0", "v_H_redrawn") if all(kx in q for q in parts)]
     for kx in TENSOR_KEYS + ["p_x", "pluck_mask"] + extra:
         out[kx] = torch.cat([q[kx] for q in parts], 0)
     out["B"] = sum(q["B"] for q in parts)
+    if all(q.get("f0_inf_corrected") is not None for q in parts):
+        out["f0_inf_corrected"] = min(q["f0_inf_corrected"] for q in parts)
     return out
 
 

@@ -98,7 +98,8 @@ def get_masks(model_name, bs):
 
 
 def sample_reference(batch_size, model_name, sr, length, theta_t, f0_inf, alpha_inf, lambda_c, precision='double',
-                     string_kwargs=None, bow_kwargs=None, hammer_kwargs=None, manufactured=False, relative_order=4):
+                     string_kwargs=None, bow_kwargs=None, hammer_kwargs=None, manufactured=False, relative_order=4,
+                     redraw_v_H=False):
     """One reference batch, drawn from the GLOBAL torch RNG exactly like reference ``simulate()`` does
     (src/task/simulate.py:148-162).  Returns the compact dict of ``sampler.sample_nsynth_like`` (CPU float64 tensors),
     plus ``target_f0_a/_b`` (the un-corrected end points) and ``u0`` (the initial displacement row)."""
@@ -260,8 +261,13 @@ def sample_reference(batch_size, model_name, sr, length, theta_t, f0_inf, alpha_
     else:
         alpha_H = hk['alpha_fixed'] * ones()
 
+    # task.load_config with a hammer-v_H profile: Hammer.dump_parameter('v_H', profile) runs initialize_velocity again
+    # (simulator.py:555-581), i.e. draws the strike velocities a second time after every other draw of the batch
+    v_H_redrawn = _ru(hk['v_H_min'], hk['v_H_max'], (Bs,), dt) if redraw_v_H else v_H
+
     D = lambda t: t.to(torch.float64)
     return dict(
+        v_H_redrawn=D(v_H_redrawn), f0_inf_corrected=float(f0_inf),
         B=Bs, sr=sr, Nt=Nt, k=k, theta_t=theta_t, lambda_c=lambda_c, relative_order=relative_order,
         Nx_t1=int(Nx_t) + 1, Nx_l1=int(Nx_l) + 1, bow_mask=bow_mask, hammer_mask=hammer_mask, pluck_mask=pluck_mask,
         kappa=D(kappa), alpha=D(alpha), pos=D(pos), T60=D(T60), p_a=D(p_a_out), p_x=D(p_x), state_u=D(state_u), state_z=D(state_z),
