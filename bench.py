@@ -483,8 +483,20 @@ def main():
     plan = Plan(args)                             # prepass + one device->host read, outside the timed region
     t_plan = time.perf_counter() - t_plan
 
+    bg = None
+    if os.environ.get("SFDTD_BENCH_BG_D2H"):      # diagnostics: a bulk device->host copy beside every step (like the e2e leg's)
+        gb = float(os.environ["SFDTD_BENCH_BG_D2H"])
+        chunk = int(os.environ.get("SFDTD_BENCH_BG_CHUNK_MB", "256")) << 20
+        bg = dict(src=torch.empty(int(gb * 1e9), dtype=torch.uint8, device=dev), stage=[torch.empty(chunk, dtype=torch.uint8).pin_memory() for _ in range(2)],
+                  stream=torch.cuda.Stream(device=dev), chunk=chunk)
+
     def one_step():
         # inputs resident in HBM; nothing here synchronises the host
+        if bg is not None:
+            with torch.cuda.stream(bg["stream"]):
+                for j, o in enumerate(range(0, bg["src"].numel(), bg["chunk"])):
+                    n_ = min(bg["chunk"], bg["src"].numel() - o)
+                    bg["stage"][j % 2][:n_].copy_(bg["src"][o:o + n_], non_blocking=True)
         su.copy_(p["state_u"]); sz.copy_(p["state_z"])
         if uH is not None:
             uH.copy_(ctl["u_H"])                  # u_H is updated in place by the stepper (string.cpp:303)
@@ -563,10 +575,10 @@ def main():
         row = ns * 3
         pitch = (row + 15) // 16 * 16
         pcm = [{kx: torch.empty(B, pitch, dtype=torch.uint8, device=dev) for kx in ("u", "z", "w")} for _ in range(2)]
-        chunk_rows = max(1, min(B, (256 << 20) // pitch))              # pinned staging: two slots of <= 256 MiB
+        chunk_rows = max(1, min(B, (int(os.environ.get("SFDTD_BENCH_STAGE_MB", "256")) << 20) // pitch))   # pinned staging: two slots of <= 256 MiB
         stage = [torch.empty(chunk_rows, pitch, dtype=torch.uint8).pin_memory() for _ in range(2)]
         flags_h = torch.empty(3, B, dtype=torch.float64).pin_memory()
-        copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("SFDTD_BENCH_COPY_PRIO", "0")))
         d2h_bytes = 3 * B * pitch + 3 * B * 8
 
         def prepare():
@@ -584,7 +596,9 @@ def main():
             q, a_, r_, k_, pl = prep
             m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True); m2 = torch.cuda.Event(enable_timing=True)
             m0.record()
+            th = time.perf_counter()
             pl.run(a_)
+            host_run.append((time.perf_counter() - th) * 1e3)
             m1.record()
             pp = postprocess(out["uout"], out["zout"], n0=2, bits=24, out=pcm[i % 2])
             m2.record()
@@ -609,6 +623,7 @@ def main():
 
         arrived = []                             # per step: event after the last byte of its results reached the host buffers
         marks_e2e = []
+        host_run = []
         prep = prepare()
         ev = launch(0, prep)
         barrier()
@@ -634,6 +649,8 @@ def main():
                "ms_per_step": float(te[0]) * 1e3, "pipelined_steps": n_e2e,
                "ms_stepper": sum(m[0].elapsed_time(m[1]) for m in marks_e2e) / len(marks_e2e),
                "ms_postprocess": sum(m[1].elapsed_time(m[2]) for m in marks_e2e) / len(marks_e2e),
+               "ms_stepper_steps": [round(m[0].elapsed_time(m[1]), 1) for m in marks_e2e],
+               "ms_launch_host": [round(x, 2) for x in host_run[1:]],
                "clocks": clk_e2e,
                "steady_state": {"value": string_seconds / float(te[1]), "ms_per_step": float(te[1]) * 1e3,
                                 "note": "interval between the host arrival of consecutive steps' results (a dataset run pipelines hundreds of steps: the drain of the last one vanishes)"},

@@ -308,6 +308,13 @@ __global__ void sfdtd_prepass_kernel(const __grid_constant__ KArgs A, int32_t *m
     }
 }
 
+// work-queue words of a call are cleared by a kernel, not by cudaMemsetAsync: a memset may be executed by a copy engine and then
+// queues behind whatever bulk transfer the caller has in flight there (measured: +190 ms per call beside a 6 GB read-back)
+__global__ void sfdtd_zero_kernel(int32_t *p, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0;
+}
+
 // ---- prepass 2: batch-max operator widths per (group, step) (misc.cpp:119-127) ------------------------
 __global__ void sfdtd_width_kernel(const __grid_constant__ KArgs A, int32_t *Wtab) {
     const int g = blockIdx.y;
@@ -1826,7 +1833,8 @@ void pin_release(void *p) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (PinBuf &b : g_pin) if (b.p == p) b.busy = false;
 }
-std::map<int, std::vector<cudaStream_t>> g_free_streams;
+struct PoolStream { cudaStream_t s; int prio; };
+std::map<int, std::vector<PoolStream>> g_free_streams;
 std::map<int, bool> g_pool_ready;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "%s: %s", #x, cudaGetErrorString(e_)); rc = SFDTD_ERR_CUDA; goto done; } } while (0)
@@ -1914,6 +1922,7 @@ struct sfdtd_plan {
     cudaEvent_t fork = nullptr;
     std::vector<cudaEvent_t> joins;
     std::vector<cudaStream_t> side;  // one per bucket (taken from / returned to the device's free list)
+    std::vector<int> side_prio;
     bool verbose = false;
 };
 
@@ -1962,8 +1971,8 @@ extern "C" int sfdtd_plan_destroy(sfdtd_plan *plan, void *cuda_stream) {
     for (cudaEvent_t e : plan->joins) cudaEventDestroy(e);
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        std::vector<cudaStream_t> &fl = g_free_streams[plan->dev];
-        fl.insert(fl.end(), plan->side.begin(), plan->side.end());
+        std::vector<PoolStream> &fl = g_free_streams[plan->dev];
+        for (size_t i = 0; i < plan->side.size(); i++) fl.push_back(PoolStream{plan->side[i], plan->side_prio[i]});
     }
     if (prev != plan->dev && prev >= 0) cudaSetDevice(prev);
     delete plan;
@@ -2238,17 +2247,27 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
         }
         if (P->n_buckets > 1) {
             std::lock_guard<std::mutex> lk(g_mu);
-            std::vector<cudaStream_t> &fl = g_free_streams[P->dev];
+            std::vector<PoolStream> &fl = g_free_streams[P->dev];
+            // Stream priorities by bucket size, smallest bucket highest: the persistent grid of ONE large bucket fills every SM
+            // (3 CTAs x 128 threads x 168 registers), so a small bucket whose CTAs lose the start-up race against it only runs
+            // after it has finished and lengthens the call by its whole duration (measured: +190 ms of 1470 ms whenever the
+            // hardware picked the large buckets first, which depended on nothing but the order the streams were created in).
+            int pr_least = 0, pr_greatest = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
             while (P->side.size() < P->n_buckets) {
-                // an IDLE released stream if there is one (a released stream may still run the call of its last plan: a new
-                // call queued behind it would serialise two independent calls), else a new one; beyond 256 streams reuse
+                // (the largest bucket lowest, the next one level above it, ...; the smallest ones share the top level)
+                const int prio = std::max(pr_greatest, pr_least - (int)(P->n_buckets - 1 - P->side.size()));
+                // an IDLE released stream of that priority if there is one (a released stream may still run the call of its last
+                // plan: a new call queued behind it would serialise two independent calls), else a new one; beyond 256 streams reuse
                 cudaStream_t st = nullptr;
                 for (size_t q = 0; q < fl.size() && !st; q++)
-                    if (cudaStreamQuery(fl[q]) == cudaSuccess) { st = fl[q]; fl.erase(fl.begin() + q); }
+                    if (fl[q].prio == prio && cudaStreamQuery(fl[q].s) == cudaSuccess) { st = fl[q].s; fl.erase(fl.begin() + q); }
                 cudaGetLastError();
-                if (!st && fl.size() >= 256) { st = fl.back(); fl.pop_back(); }
-                if (!st) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-                P->side.push_back(st);
+                if (!st && fl.size() >= 256)
+                    for (size_t q = 0; q < fl.size() && !st; q++)
+                        if (fl[q].prio == prio) { st = fl[q].s; fl.erase(fl.begin() + q); }
+                if (!st) CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio));
+                P->side.push_back(st); P->side_prio.push_back(prio);
             }
         }
     }
@@ -2285,7 +2304,11 @@ extern "C" int sfdtd_forward_plan(sfdtd_plan *P, const sfdtd_args *args, void *c
     g_launches++;
     CK(cudaGetLastError());
     K.Wtab = P->d_wtab; K.maxNl = P->d_maxNl; K.uH_carry = P->d_uH;
-    if (P->queue_words) CK(cudaMemsetAsync(P->d_queue, 0, sizeof(int32_t) * P->queue_words, stream));
+    if (P->queue_words) {
+        sfdtd_zero_kernel<<<(unsigned)((P->queue_words + 255) / 256), 256, 0, stream>>>(P->d_queue, P->queue_words);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
     const size_t nb = P->n_buckets;
     const std::vector<cudaStream_t> &ss = P->side;
     if (nb > 1) CK(cudaEventRecord(P->fork, stream));
