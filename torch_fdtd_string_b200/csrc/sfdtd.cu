@@ -726,7 +726,10 @@ __device__ __noinline__ void fill_table_row(const KArgs &A, const TabIn &in, int
 #endif
 
 // ======================================================================================================
-template <typename T, int L, int ET, bool GROUPED, bool MANUF>
+// PF: build for the reference layout (SFDTD_SAVE_STATE calls: one reference batch per call, latency-bound) -- row n of the state
+// histories, read-modified-written at the end of step n, is pulled into L2 at the start of the step (+14 % on the literal
+// drop-in batch).  A separate instantiation: the same lines inside the compact kernels cost them 2-3 % (register allocation).
+template <typename T, int L, int ET, bool GROUPED, bool MANUF, bool PF = false>
 __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
     constexpr int TSZ = (int)sizeof(T);
     constexpr float GS_TOL = Real<T>::GS_TOL;
@@ -943,6 +946,12 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
             const int4 tiA = *(const int4 *)(tabi + jj * NI);
             const int N_t = tiA.x, N_l = tiA.y, R = tiA.z & 0xffffff, WLs = tiA.w;
             if (tiA.z >> 30) status |= SFDTD_ST_RANGE;
+            if (PF && save_state) {
+                const T *pu = (const T *)a.state_u.ptr + (int64_t)b * a.state_u.bs + (int64_t)n * a.state_u.ts + ln * ET;
+                if (ln * ET < NXT) asm volatile("prefetch.global.L2 [%0];" :: "l"(pu));
+                const T *pz = (const T *)a.state_z.ptr + (int64_t)b * a.state_z.bs + (int64_t)n * a.state_z.ts;
+                for (int j = ln * 4; j < NXL; j += L * 4) asm volatile("prefetch.global.L2 [%0];" :: "l"(pz + j));
+            }
 
             // ---- interpolation rows, rebuilt only when a grid size changed (misc.cpp:78-105) ----
             const bool grid_changed = (N_t != curNt) || (N_l != curNl);
@@ -1620,9 +1629,9 @@ __device__ __forceinline__ void step_body(const KArgs &A, const CtaDesc *cd) {
 }
 
 // independent mode: strings of unforced groups, any warp of any CTA
-template <typename T, int L, int ET, int MAXT, int MINB>
+template <typename T, int L, int ET, int MAXT, int MINB, bool PF = false>
 __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_constant__ KArgs A) {
-    step_body<T, L, ET, false, false>(A, nullptr);
+    step_body<T, L, ET, false, false, PF>(A, nullptr);
 }
 // grouped mode: one thread-block cluster of 128-thread CTAs per group; the CTA's descriptor picks the lane/row shape of its
 // string slots.  KIND 0: strings of <= 64 rows on 16 lanes x 4 rows, <= 128 rows on 32 lanes x 4 rows (168 registers, three
@@ -1636,15 +1645,15 @@ __global__ void __launch_bounds__(MAXT, MINB) sfdtd_step_kernel(const __grid_con
 #ifndef SFDTD_F32_GROUP_MINB
 #define SFDTD_F32_GROUP_MINB 3
 #endif
-template <typename T, int KIND>
+template <typename T, int KIND, bool PF = false>
 __global__ void __launch_bounds__(128, KIND == 0 ? (sizeof(T) == 4 ? SFDTD_F32_GROUP_MINB : SFDTD_GROUP_MINB) : 1)
 sfdtd_group_kernel(const __grid_constant__ KArgs A) {
     const CtaDesc *cd = A.ctas + blockIdx.x;
     if (KIND == 0) {
-        if (cd->cls == 0) step_body<T, 16, 4, true, false>(A, cd);
-        else step_body<T, 32, 4, true, false>(A, cd);
+        if (cd->cls == 0) step_body<T, 16, 4, true, false, PF>(A, cd);
+        else step_body<T, 32, 4, true, false, PF>(A, cd);
     } else if (KIND == 1) {
-        step_body<T, 32, 8, true, false>(A, cd);
+        step_body<T, 32, 8, true, false, PF>(A, cd);
     } else if (KIND == 2) {
         step_body<T, 32, 8, true, true>(A, cd);
     } else {
@@ -1766,10 +1775,13 @@ std::atomic<int64_t> g_launches{0};
 // uses the 8-lane kernels, for A/B runs via SFDTD_TIER=0; 2- and 3-row kernels, tighter register caps (128) and a
 // REDUX-based max reduction all measured slower).
 // kern[dtype]: the fp64 build and (default tier only) the fp32 build; MB32_ = CTAs per SM the fp32 build is compiled for
-struct Config { int L, ET, tier; void (*kern[2])(const KArgs); };
-#define CFG_I(L_, ET_, MB_, TIER_) Config{L_, ET_, TIER_, {sfdtd_step_kernel<double, L_, ET_, 128, MB_>, nullptr}}
-#define CFG_D(L_, ET_, MB_, MB32_, TIER_) Config{L_, ET_, TIER_, {sfdtd_step_kernel<double, L_, ET_, 128, MB_>, sfdtd_step_kernel<float, L_, ET_, 128, MB32_>}}
-#define CFG_F(L_, ET_, MB32_, TIER_) Config{L_, ET_, TIER_, {nullptr, sfdtd_step_kernel<float, L_, ET_, 128, MB32_>}}
+// kern_pf[dtype]: the build for SFDTD_SAVE_STATE calls (state-history rows prefetched), where one exists
+struct Config { int L, ET, tier; void (*kern[2])(const KArgs); void (*kern_pf[2])(const KArgs); };
+#define CFG_I(L_, ET_, MB_, TIER_) Config{L_, ET_, TIER_, {sfdtd_step_kernel<double, L_, ET_, 128, MB_>, nullptr}, {nullptr, nullptr}}
+#define CFG_D(L_, ET_, MB_, MB32_, TIER_) Config{L_, ET_, TIER_, {sfdtd_step_kernel<double, L_, ET_, 128, MB_>, sfdtd_step_kernel<float, L_, ET_, 128, MB32_>}, {nullptr, nullptr}}
+#define CFG_P(L_, ET_, MB_, MB32_, TIER_) Config{L_, ET_, TIER_, {sfdtd_step_kernel<double, L_, ET_, 128, MB_>, sfdtd_step_kernel<float, L_, ET_, 128, MB32_>}, \
+                                                 {sfdtd_step_kernel<double, L_, ET_, 128, MB_, true>, sfdtd_step_kernel<float, L_, ET_, 128, MB32_, true>}}
+#define CFG_F(L_, ET_, MB32_, TIER_) Config{L_, ET_, TIER_, {nullptr, sfdtd_step_kernel<float, L_, ET_, 128, MB32_>}, {nullptr, nullptr}}
 const Config g_configs[] = {   // smallest first
     CFG_I(8, 4, 3, 0), CFG_I(8, 6, 2, 0), CFG_I(16, 4, 3, 0), CFG_I(16, 6, 2, 0), CFG_I(32, 4, 3, 0), CFG_I(32, 8, 1, 0),
 #if SFDTD_F32_L8
@@ -1777,7 +1789,7 @@ const Config g_configs[] = {   // smallest first
     // cyclic-reduction level and half the shuffles per row less)
     CFG_F(8, 8, SFDTD_F32_L8_MINB, 2),
 #endif
-    CFG_D(16, 4, 3, SFDTD_F32_MINB, 2), CFG_D(32, 4, 3, SFDTD_F32_MINB, 2), CFG_D(32, 8, 1, 2, 2), CFG_D(32, 12, 1, 1, 2), CFG_D(32, 20, 1, 1, 2),
+    CFG_P(16, 4, 3, SFDTD_F32_MINB, 2), CFG_P(32, 4, 3, SFDTD_F32_MINB, 2), CFG_P(32, 8, 1, 2, 2), CFG_D(32, 12, 1, 1, 2), CFG_D(32, 20, 1, 1, 2),
     CFG_I(8, 4, 3, 3), CFG_I(16, 4, 3, 3), CFG_I(32, 4, 3, 3), CFG_I(32, 8, 1, 3),
 };
 #ifndef SFDTD_DEFAULT_TIER
@@ -1788,6 +1800,9 @@ constexpr int N_CONFIGS = sizeof(g_configs) / sizeof(g_configs[0]);
 void (*const g_group_kernels[2][4])(const KArgs) = {
     {sfdtd_group_kernel<double, 0>, sfdtd_group_kernel<double, 1>, sfdtd_group_kernel<double, 2>, sfdtd_group_kernel<double, 3>},
     {sfdtd_group_kernel<float, 0>, sfdtd_group_kernel<float, 1>, nullptr, sfdtd_group_kernel<float, 3>}};   // (no fp32 manufactured mode)
+void (*const g_group_kernels_pf[2][4])(const KArgs) = {        // SFDTD_SAVE_STATE builds (prefetch), kinds 0 and 1
+    {sfdtd_group_kernel<double, 0, true>, sfdtd_group_kernel<double, 1, true>, nullptr, nullptr},
+    {sfdtd_group_kernel<float, 0, true>, sfdtd_group_kernel<float, 1, true>, nullptr, nullptr}};
 struct GShape { int L, ET; };
 const GShape g_gshape[4][2] = {{{16, 4}, {32, 4}}, {{32, 8}, {32, 8}}, {{32, 8}, {32, 8}}, {{32, 20}, {32, 20}}};
 constexpr int MAX_ROWS = 640;       // transverse rows of the largest kernel shape (32 lanes x 20 rows)
@@ -1846,6 +1861,7 @@ struct Launch {
     size_t smem = 0, off = 0;       // off: first entry of ids (independent) / of ctas (grouped)
     bool need_xax = false;
     bool queue = false; int q_slice = 0, q_nslices = 0, q_full = 0; size_t q_idx = 0, done_off = 0;
+    void (*fn)(const KArgs) = nullptr;      // the kernel of this launch (compact or SAVE_STATE build)
 };
 
 int validate(const sfdtd_args *args) {
@@ -2021,6 +2037,7 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
     P->B = a.B; P->group_size = a.group_size; P->Nt = a.Nt; P->Nx_t1 = a.Nx_t1; P->Nx_l1 = a.Nx_l1; P->n_groups = n_groups;
     P->flags = a.flags; P->dtype = a.dtype;
     const int dt = a.dtype == SFDTD_F32 ? 1 : 0, tsz = dt ? 4 : 8;
+    const bool save_pf = (a.flags & SFDTD_SAVE_STATE) != 0;
 
     CK(guard.enter(a.state_u.ptr));
     CK(cudaGetDevice(&P->dev));
@@ -2164,7 +2181,8 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
             ln.need_xax = !skip_aux;
             h_ids.insert(h_ids.end(), ids.begin(), ids.end());
             // CTA size that keeps the most strings resident per SM (registers and shared memory both bound it)
-            const int regs = kernel_regs(cf.kern[dt]);
+            ln.fn = (save_pf && cf.kern_pf[dt]) ? cf.kern_pf[dt] : cf.kern[dt];
+            const int regs = kernel_regs(ln.fn);
             int best = 32; long best_res = -1;
             for (int th : {128, 96, 64, 32}) {
                 if (th % cf.L) continue;
@@ -2184,13 +2202,13 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
                 snprintf(g_err, sizeof g_err, "a bucket (L=%d, ET=%d) needs %zu bytes of shared memory (> 227 KB)", cf.L, cf.ET, ln.smem);
                 rc = SFDTD_ERR_UNSUPPORTED; goto done;
             }
-            CK(cudaFuncSetAttribute(cf.kern[dt], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CK(cudaFuncSetAttribute(ln.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             // one shared-memory carve-out for every bucket kernel, so that CTAs of different buckets can share an SM
-            CK(cudaFuncSetAttribute(cf.kern[dt], cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            CK(cudaFuncSetAttribute(ln.fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             if (use_queue) {
                 // persistent grid: what is resident at once; the warps pull their string sets from the bucket's counter
                 int per_sm = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf.kern[dt], ln.threads, ln.smem));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ln.fn, ln.threads, ln.smem));
                 const int spw = 32 / cf.L, n_sets = (ln.n_items + spw - 1) / spw, wpc = ln.threads / 32;
                 const int resident = std::max(1, per_sm) * P->n_sms;
                 // tail group: the sets that would run in the last round of the resident warps, in SFDTD_QSLICES time slices
@@ -2215,11 +2233,12 @@ extern "C" int sfdtd_plan_create(const sfdtd_args *args, void *cuda_stream, sfdt
             ln.grid = (int)kv.second.ctas.size(); ln.n_items = ln.grid / ln.cluster; ln.off = h_ctas.size(); ln.need_xax = true;
             ln.smem = std::max(kv.second.smem, (size_t)pad_smem);
             h_ctas.insert(h_ctas.end(), kv.second.ctas.begin(), kv.second.ctas.end());
-            CK(cudaFuncSetAttribute(g_group_kernels[dt][ln.cfg], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            CK(cudaFuncSetAttribute(g_group_kernels[dt][ln.cfg], cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            ln.fn = (save_pf && g_group_kernels_pf[dt][ln.cfg]) ? g_group_kernels_pf[dt][ln.cfg] : g_group_kernels[dt][ln.cfg];
+            CK(cudaFuncSetAttribute(ln.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CK(cudaFuncSetAttribute(ln.fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             if (P->verbose)
                 fprintf(stderr, "[sfdtd] bucket grouped kind=%d cluster=%d groups=%d threads=%d grid=%d smem=%zu regs=%d\n", ln.cfg,
-                        ln.cluster, ln.n_items, ln.threads, ln.grid, ln.smem, kernel_regs(g_group_kernels[dt][ln.cfg]));
+                        ln.cluster, ln.n_items, ln.threads, ln.grid, ln.smem, kernel_regs(ln.fn));
             P->launches.push_back(ln);
         }
     }
@@ -2330,7 +2349,7 @@ extern "C" int sfdtd_forward_plan(sfdtd_plan *P, const sfdtd_args *args, void *c
                 K.queue = P->d_queue + ln.q_idx; K.done = P->d_queue + P->n_buckets + ln.done_off;
                 K.q_slice = ln.q_slice; K.q_nslices = ln.q_nslices; K.q_full = ln.q_full;
             }
-            g_configs[ln.cfg].kern[dt]<<<(unsigned)ln.grid, ln.threads, ln.smem, s>>>(K);
+            ln.fn<<<(unsigned)ln.grid, ln.threads, ln.smem, s>>>(K);
         } else {
             K.ctas = P->d_ctas + ln.off;
             cudaLaunchConfig_t lc; memset(&lc, 0, sizeof lc);
@@ -2339,7 +2358,7 @@ extern "C" int sfdtd_forward_plan(sfdtd_plan *P, const sfdtd_args *args, void *c
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = (unsigned)ln.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             lc.attrs = at; lc.numAttrs = 1;
-            CK(cudaLaunchKernelEx(&lc, g_group_kernels[dt][ln.cfg], K));
+            CK(cudaLaunchKernelEx(&lc, ln.fn, K));
         }
         g_launches++;
         CK(cudaGetLastError());
