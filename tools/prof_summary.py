@@ -47,7 +47,7 @@ if "group_kernel" in d["Kernel Name"]:
     mangled = "sfdtd_group_kernelI" + ty[m.group(1)] + "Li" + m.group(2) + "E"
 else:
     kn = re.search(r"<(double|float), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d)>", d["Kernel Name"]).groups()
-    mangled = f"sfdtd_step_kernelI{ty[kn[0]]}Li{kn[1]}ELi{kn[2]}ELi{kn[3]}ELi{kn[4]}EEE"
+    mangled = f"sfdtd_step_kernelI{ty[kn[0]]}Li{kn[1]}ELi{kn[2]}ELi{kn[3]}ELi{kn[4]}ELb0EEE"
 start = [i for i, l in enumerate(li) if l.startswith(".text.") and mangled in l][0]
 end = next(i for i in range(start + 1, len(li)) if li[i].startswith("//-----"))
 cur, lines = None, []

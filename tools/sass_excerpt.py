@@ -31,7 +31,7 @@ cubin = [x for x in os.listdir(tmp) if x.endswith(".cubin")][0]
 li = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
 for ty, name in (("d", "f64"), ("f", "f32")):
     heads = [i for i, l in enumerate(li) if l.startswith("//--------------------- .text.")]
-    start = [i for i in heads if f"sfdtd_step_kernelI{ty}Li16ELi4ELi128" in li[i]][0]
+    start = [i for i in heads if f"sfdtd_step_kernelI{ty}Li16ELi4ELi128" in li[i] and "Lb0E" in li[i]][0]      # the compact build (PF = false)
     end = min([i for i in heads if i > start] + [len(li)])
     cur, rows, mix = None, [], collections.Counter()
     for l in li[start:end]:
