@@ -42,12 +42,14 @@ subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, capture_output=True)
 cubin = [x for x in os.listdir(tmp) if x.endswith(".cubin")][0]
 li = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
 ty = {"double": "d", "float": "f"}
+BOOL = r"(?:, \(?(?:bool\))?(\d|true|false))?"              # the PF template argument (absent in captures before it existed)
+pf = lambda v: "1" if v in ("1", "true") else "0"
 if "group_kernel" in d["Kernel Name"]:
-    m = re.search(r"group_kernel<(double|float), \(?(?:int\))?(\d)>", d["Kernel Name"])
-    mangled = "sfdtd_group_kernelI" + ty[m.group(1)] + "Li" + m.group(2) + "E"
+    m = re.search(r"group_kernel<(double|float), \(?(?:int\))?(\d)" + BOOL + ">", d["Kernel Name"])
+    mangled = "sfdtd_group_kernelI" + ty[m.group(1)] + "Li" + m.group(2) + "ELb" + pf(m.group(3)) + "E"
 else:
-    kn = re.search(r"<(double|float), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d)>", d["Kernel Name"]).groups()
-    mangled = f"sfdtd_step_kernelI{ty[kn[0]]}Li{kn[1]}ELi{kn[2]}ELi{kn[3]}ELi{kn[4]}ELb0EEE"
+    kn = re.search(r"<(double|float), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d)" + BOOL + ">", d["Kernel Name"]).groups()
+    mangled = f"sfdtd_step_kernelI{ty[kn[0]]}Li{kn[1]}ELi{kn[2]}ELi{kn[3]}ELi{kn[4]}ELb{pf(kn[5])}EEE"
 start = [i for i, l in enumerate(li) if l.startswith(".text.") and mangled in l][0]
 end = next(i for i in range(start + 1, len(li)) if li[i].startswith("//-----"))
 cur, lines = None, []
